@@ -1,0 +1,350 @@
+// Small CUDA-core kernels around the tensor-core path: first/last convolutions (4 channels), time
+// embedding, small-M fp32 linears, casts / nearest upsample, CFG + DDIM update.
+#include "../../include/adaface_b200.h"
+#include "common.cuh"
+
+namespace af {
+
+// ---------------------------------------------------------------------------------------------
+// conv_in: NCHW fp32 [B,Cin,H,W] (Cin small) -> NHWC fp32 [B,H,W,Cout], 3x3 pad 1, fp32 math.
+// Reference: UNetModel.input_blocks[0] = conv_nd(2, 4, 320, 3, padding=1) (openaimodel.py:527-533).
+// block = one row segment of 16 pixels; thread <-> output channel.
+// ---------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(320) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, float* __restrict__ y, int B,
+                                                      int H, int W, int Cout) {
+  constexpr int TP = 16;
+  __shared__ float patch[CIN][3][TP + 2];
+  const int wt = blockIdx.x * TP;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  for (int i = threadIdx.x; i < CIN * 3 * (TP + 2); i += blockDim.x) {
+    const int c = i / (3 * (TP + 2));
+    const int rr = (i / (TP + 2)) % 3;
+    const int cc = i % (TP + 2);
+    const int hh = h + rr - 1, ww = wt + cc - 1;
+    float v = 0.f;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((static_cast<size_t>(b) * CIN + c) * H + hh) * W + ww];
+    patch[c][rr][cc] = v;
+  }
+  __syncthreads();
+  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+    float wr[CIN * 9];
+#pragma unroll
+    for (int i = 0; i < CIN * 9; ++i) wr[i] = w[co * CIN * 9 + i];  // [co][ci][ky][kx]
+    const float bv = bias ? bias[co] : 0.f;
+    for (int px = 0; px < TP && wt + px < W; ++px) {
+      float acc = bv;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) acc += wr[(c * 3 + ky) * 3 + kx] * patch[c][ky][px + kx];
+      y[((static_cast<size_t>(b) * H + h) * W + wt + px) * Cout + co] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv_out: NHWC bf16 [B,H,W,C] -> NCHW fp32 [B,COUT,H,W], 3x3 pad 1; warp per output pixel.
+// Reference: UNetModel.out[-1] = conv_nd(2, 320, 4, 3, padding=1) (openaimodel.py:693-697).
+// Weights pre-packed fp32 [COUT][3][3][C] and staged in shared memory.
+// ---------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(256) conv_out_kernel(const __nv_bfloat16* __restrict__ x,
+                                                       const float* __restrict__ w, const float* __restrict__ bias,
+                                                       float* __restrict__ y, int B, int H, int W, int C) {
+  extern __shared__ float sw[];  // [COUT*9*C]
+  for (int i = threadIdx.x; i < COUT * 9 * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const long long total = static_cast<long long>(B) * H * W;
+  const int nvec = C >> 3;
+  for (long long pix = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); pix < total;
+       pix += static_cast<long long>(gridDim.x) * warps_per_block) {
+    const int wq = static_cast<int>(pix % W);
+    const int hq = static_cast<int>((pix / W) % H);
+    const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    float acc[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hh = hq + tap / 3 - 1, ww = wq + tap % 3 - 1;
+      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+      const uint4* xp = reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + hh) * W + ww) * C);
+      for (int k = lane; k < nvec; k += 32) {
+        const uint4 raw = __ldg(xp + k);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        float xv[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(h2[e]);
+          xv[2 * e] = f.x;
+          xv[2 * e + 1] = f.y;
+        }
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+          const float* wp = sw + (o * 9 + tap) * C + k * 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[o] += xv[e] * wp[e];
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = warp_sum(acc[o]);
+    if (lane < COUT) {
+      float v = 0.f;
+#pragma unroll
+      for (int o = 0; o < COUT; ++o)
+        if (lane == o) v = acc[o];
+      y[((static_cast<size_t>(b) * COUT + lane) * H + hq) * W + wq] = v + (bias ? bias[lane] : 0.f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sinusoidal timestep embedding (ldm/modules/diffusionmodules/util.py:154-174): [cos | sin], fp32
+// ---------------------------------------------------------------------------------------------
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int B, int dim) {
+  const int half = dim >> 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, j = i - b * half;
+  const float freq = expf(-9.210340371976184f * static_cast<float>(j) / static_cast<float>(half));  // ln(10000)
+  const float arg = t[b] * freq;
+  out[static_cast<size_t>(b) * dim + j] = cosf(arg);
+  out[static_cast<size_t>(b) * dim + half + j] = sinf(arg);
+  if ((dim & 1) && j == 0) out[static_cast<size_t>(b) * dim + dim - 1] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small-M fp32 linear: y[M,N] = act_out(act_in(x)[M,K] @ W[N,K]^T + b).  One warp per output feature.
+// Used for time_embed (openaimodel.py:518-522,847) and the 22 ResBlock emb_layers (:222-228,268), whose
+// weights are concatenated into one [sum Cout, 1280] matrix at load time.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) linear_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ y,
+                                                           int M, int N, int K, int silu_in, int silu_out) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const float4* wr = reinterpret_cast<const float4*>(w + static_cast<size_t>(n) * K);
+  const int nvec = K >> 2;
+  for (int m0 = 0; m0 < M; m0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int k = lane; k < nvec; k += 32) {
+      const float4 wv = __ldg(wr + k);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (m0 + i < M) {
+          float4 xv = __ldg(reinterpret_cast<const float4*>(x + static_cast<size_t>(m0 + i) * K) + k);
+          if (silu_in) {
+            xv.x = silu_f(xv.x); xv.y = silu_f(xv.y); xv.z = silu_f(xv.z); xv.w = silu_f(xv.w);
+          }
+          acc[i] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float s = warp_sum(acc[i]);
+      if (lane == 0 && m0 + i < M) {
+        float v = s + (bias ? bias[n] : 0.f);
+        if (silu_out) v = silu_f(v);
+        y[static_cast<size_t>(m0 + i) * N + n] = v;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 -> bf16 cast, optional nearest 2x upsample (Upsample, openaimodel.py:120 F.interpolate nearest)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                        size_t n4) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(y)[i] = pk;
+  }
+}
+
+__global__ void __launch_bounds__(256) upsample2x_cast_kernel(const float* __restrict__ x,
+                                                              __nv_bfloat16* __restrict__ y, int B, int H, int W,
+                                                              int C) {
+  const int cq = C >> 2;
+  const size_t total = static_cast<size_t>(B) * H * W * cq;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % cq);
+    const size_t pix = i / cq;
+    const int w = static_cast<int>(pix % W);
+    const int h = static_cast<int>((pix / W) % H);
+    const int b = static_cast<int>(pix / (static_cast<size_t>(W) * H));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    const size_t W2 = 2 * static_cast<size_t>(W);
+    const size_t base = ((static_cast<size_t>(b) * 2 * H + 2 * h) * W2 + 2 * w) * cq + c4;
+    uint2* yo = reinterpret_cast<uint2*>(y);
+    yo[base] = pk;
+    yo[base + cq] = pk;
+    yo[base + W2 * cq] = pk;
+    yo[base + W2 * cq + cq] = pk;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CFG combine + DDIM update (ldm/models/diffusion/ddim.py:260,279,283,295), same fp32 operation order as
+// the reference so that given identical eps the update is bit-exact:
+//   e      = e_u + g * (e_c - e_u)
+//   pred   = (x - sqrt(1-a_t) * e) / sqrt(a_t)
+//   dir    = sqrt(1 - a_prev - sigma^2) * e
+//   x_prev = sqrt(a_prev) * pred + dir + sigma * noise * temperature
+// coef row: [g, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef, sigma*temperature, 0, 0]
+// eps holds the conditional half first, then the unconditional half (ddim.py:238-243); n = elements per half.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cfg_ddim_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                                       int has_uncond, const float* __restrict__ noise,
+                                                       const float* __restrict__ coef_table,
+                                                       const int* __restrict__ step_idx, float* __restrict__ x_prev,
+                                                       float* __restrict__ pred_x0, size_t n) {
+  const float* cf = coef_table + (step_idx ? static_cast<size_t>(*step_idx) * 8 : 0);
+  const float g = cf[0], s1m = cf[1], sat = cf[2], sap = cf[3], dcoef = cf[4], sig = cf[5];
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float e = eps[i];
+    if (has_uncond) {
+      const float eu = eps[n + i];
+      e = __fadd_rn(eu, __fmul_rn(g, __fsub_rn(e, eu)));
+    }
+    const float pred = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(s1m, e)), sat);
+    const float dir = __fmul_rn(dcoef, e);
+    float xp = __fadd_rn(__fmul_rn(sap, pred), dir);
+    const float nz = noise ? __fmul_rn(sig, noise[i]) : 0.f;
+    xp = __fadd_rn(xp, nz);
+    x_prev[i] = xp;
+    if (pred_x0) pred_x0[i] = pred;
+  }
+}
+
+// bump the device-side step counter and publish the next timestep to t_buf[0..B)
+__global__ void advance_step_kernel(int* step_idx, const float* __restrict__ t_table, float* __restrict__ t_buf, int B,
+                                    int num_steps) {
+  __shared__ int s_next;
+  if (threadIdx.x == 0) {
+    int nx = *step_idx + 1;
+    s_next = nx;
+  }
+  __syncthreads();
+  const int nx = s_next;
+  if (nx < num_steps)
+    for (int i = threadIdx.x; i < B; i += blockDim.x) t_buf[i] = t_table[nx];
+  __syncthreads();
+  if (threadIdx.x == 0) *step_idx = nx;
+}
+
+}  // namespace af
+
+using namespace af;
+
+static inline int grid_for(size_t work_items, int threads) {
+  size_t g = (work_items + threads - 1) / threads;
+  const size_t cap = static_cast<size_t>(num_sms()) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+extern "C" int af_conv_in(const float* x_nchw, const float* w, const float* bias, float* y_nhwc, int B, int Cin, int H,
+                          int W, int Cout, cudaStream_t stream) {
+  AF_CHECK_ARG(x_nchw && w && y_nhwc, "af_conv_in: null pointer");
+  AF_CHECK_ARG(Cin == 4, "af_conv_in: Cin=%d unsupported (4)", Cin);
+  dim3 grid((W + 15) / 16, H, B);
+  const int threads = Cout >= 320 ? 320 : ((Cout + 31) / 32) * 32;
+  conv_in_kernel<4><<<grid, threads, 0, stream>>>(x_nchw, w, bias, y_nhwc, B, H, W, Cout);
+  AF_LAUNCH_CHECK("conv_in_kernel");
+  return 0;
+}
+
+extern "C" int af_conv_out(const void* x_nhwc_bf16, const float* w_packed, const float* bias, float* y_nchw, int B,
+                           int H, int W, int C, int Cout, cudaStream_t stream) {
+  AF_CHECK_ARG(x_nhwc_bf16 && w_packed && y_nchw, "af_conv_out: null pointer");
+  AF_CHECK_ARG(Cout == 4 && C % 8 == 0, "af_conv_out: Cout=%d C=%d unsupported", Cout, C);
+  const size_t smem = static_cast<size_t>(Cout) * 9 * C * sizeof(float);
+  AF_CHECK_ARG(smem <= 200 * 1024, "af_conv_out: C=%d too large", C);
+  static size_t configured = 0;
+  if (smem > configured) {
+    AF_CUDA(cudaFuncSetAttribute(conv_out_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  const long long total = static_cast<long long>(B) * H * W;
+  long long blocks = (total + 7) / 8;
+  const long long cap = static_cast<long long>(num_sms()) * 4;
+  if (blocks > cap) blocks = cap;
+  conv_out_kernel<4><<<static_cast<unsigned>(blocks), 256, smem, stream>>>(
+      static_cast<const __nv_bfloat16*>(x_nhwc_bf16), w_packed, bias, y_nchw, B, H, W, C);
+  AF_LAUNCH_CHECK("conv_out_kernel");
+  return 0;
+}
+
+extern "C" int af_timestep_embedding(const float* t, float* out, int B, int dim, cudaStream_t stream) {
+  AF_CHECK_ARG(t && out && B > 0 && dim >= 2, "af_timestep_embedding: bad args");
+  const int n = B * (dim / 2);
+  timestep_embedding_kernel<<<(n + 255) / 256, 256, 0, stream>>>(t, out, B, dim);
+  AF_LAUNCH_CHECK("timestep_embedding_kernel");
+  return 0;
+}
+
+extern "C" int af_linear_small(const float* x, const float* w, const float* bias, float* y, int M, int N, int K,
+                               int silu_in, int silu_out, cudaStream_t stream) {
+  AF_CHECK_ARG(x && w && y, "af_linear_small: null pointer");
+  AF_CHECK_ARG(M > 0 && N > 0 && K > 0 && K % 4 == 0, "af_linear_small: M=%d N=%d K=%d (K%%4)", M, N, K);
+  linear_small_kernel<<<(N + 7) / 8, 256, 0, stream>>>(x, w, bias, y, M, N, K, silu_in, silu_out);
+  AF_LAUNCH_CHECK("linear_small_kernel");
+  return 0;
+}
+
+extern "C" int af_cast_bf16(const float* x, void* y_bf16, long long n, cudaStream_t stream) {
+  AF_CHECK_ARG(x && y_bf16 && n > 0 && n % 4 == 0, "af_cast_bf16: bad args (n%%4)");
+  const size_t n4 = static_cast<size_t>(n) / 4;
+  cast_bf16_kernel<<<grid_for(n4, 256), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(y_bf16), n4);
+  AF_LAUNCH_CHECK("cast_bf16_kernel");
+  return 0;
+}
+
+extern "C" int af_upsample2x_cast(const float* x_nhwc, void* y_bf16, int B, int H, int W, int C, cudaStream_t stream) {
+  AF_CHECK_ARG(x_nhwc && y_bf16 && C % 4 == 0, "af_upsample2x_cast: bad args");
+  const size_t total = static_cast<size_t>(B) * H * W * (C / 4);
+  upsample2x_cast_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x_nhwc, static_cast<__nv_bfloat16*>(y_bf16), B, H, W, C);
+  AF_LAUNCH_CHECK("upsample2x_cast_kernel");
+  return 0;
+}
+
+extern "C" int af_cfg_ddim_update(const float* x, const float* eps, int has_uncond, const float* noise,
+                                  const float* coef_table, const int* step_idx, float* x_prev, float* pred_x0,
+                                  long long n, cudaStream_t stream) {
+  AF_CHECK_ARG(x && eps && coef_table && x_prev && n > 0, "af_cfg_ddim_update: bad args");
+  cfg_ddim_kernel<<<grid_for(static_cast<size_t>(n), 256), 256, 0, stream>>>(x, eps, has_uncond, noise, coef_table,
+                                                                              step_idx, x_prev, pred_x0,
+                                                                              static_cast<size_t>(n));
+  AF_LAUNCH_CHECK("cfg_ddim_kernel");
+  return 0;
+}
+
+extern "C" int af_advance_step(int* step_idx, const float* t_table, float* t_buf, int B, int num_steps,
+                               cudaStream_t stream) {
+  AF_CHECK_ARG(step_idx && t_table && t_buf && B > 0, "af_advance_step: bad args");
+  advance_step_kernel<<<1, 128, 0, stream>>>(step_idx, t_table, t_buf, B, num_steps);
+  AF_LAUNCH_CHECK("advance_step_kernel");
+  return 0;
+}

@@ -1,0 +1,252 @@
+"""Thin tensor-level wrappers over the C ABI (one function per af_* entry point).
+
+PyTorch is plumbing here: it owns device memory and streams; all arithmetic happens in
+libadaface_b200.so.  Every wrapper validates dtype/device/contiguity, passes raw pointers and
+raises on a non-zero return code.  No op has a CPU or eager fallback.
+"""
+from __future__ import annotations
+
+from ctypes import byref
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import AF_DTYPE_BF16, AF_DTYPE_F32, AfEpilogue
+
+_gn_ws = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous")
+
+
+def _epilogue(out: torch.Tensor, bias=None, rowbias=None, rows_per_group=0, residual=None, geglu=False,
+              ldo: int = 0, ldr: int = 0) -> AfEpilogue:
+    ep = AfEpilogue()
+    if bias is not None:
+        _chk(bias, torch.float32, "bias")
+    if rowbias is not None:
+        _chk(rowbias, torch.float32, "rowbias")
+    if residual is not None:
+        _chk(residual, torch.float32, "residual")
+    ep.bias = _p(bias)
+    ep.rowbias = _p(rowbias)
+    ep.rows_per_group = int(rows_per_group)
+    ep.residual = _p(residual)
+    ep.ldr = int(ldr)
+    ep.out = out.data_ptr()
+    ep.ldo = int(ldo)
+    if out.dtype == torch.bfloat16:
+        ep.out_dtype = AF_DTYPE_BF16
+    elif out.dtype == torch.float32:
+        ep.out_dtype = AF_DTYPE_F32
+    else:
+        raise ValueError(f"out dtype {out.dtype} unsupported")
+    ep.geglu = 1 if geglu else 0
+    return ep
+
+
+def gemm(a0: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, *, a1: Optional[torch.Tensor] = None,
+         bias=None, rowbias=None, rows_per_group=0, residual=None, geglu=False, ldo: int = 0, ldr: int = 0,
+         bn: int = 0, M: Optional[int] = None, lda0: Optional[int] = None, K0: Optional[int] = None) -> torch.Tensor:
+    """out[M, N] = [a0 | a1] @ wt^T (+ fused epilogue).  a*: bf16 [M, K*]; wt: bf16 [N, K0+K1]."""
+    lib = _lib.load()
+    _chk(wt, torch.bfloat16, "wt")
+    if a0.dtype != torch.bfloat16 or not a0.is_cuda:
+        raise ValueError("a0 must be a CUDA bf16 tensor")
+    M = int(a0.shape[0]) if M is None else M
+    K0 = int(a0.shape[-1]) if K0 is None else K0
+    lda0 = int(a0.stride(0)) if lda0 is None else lda0
+    K1, lda1 = 0, 0
+    if a1 is not None:
+        _chk(a1, torch.bfloat16, "a1")
+        K1, lda1 = int(a1.shape[-1]), int(a1.stride(0))
+    N = int(wt.shape[0])
+    if int(wt.shape[1]) != K0 + K1:
+        raise ValueError(f"wt K={wt.shape[1]} != K0+K1={K0 + K1}")
+    ep = _epilogue(out, bias, rowbias, rows_per_group, residual, geglu, ldo, ldr)
+    rc = lib.af_gemm_bf16(a0.data_ptr(), lda0, K0, _p(a1), lda1, K1, wt.data_ptr(), M, N, byref(ep), bn, _stream())
+    _lib.check(rc, "af_gemm_bf16")
+    return out
+
+
+def conv3x3(x0: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, *, x1: Optional[torch.Tensor] = None, stride=1,
+            bias=None, rowbias=None, residual=None, bn: int = 0) -> torch.Tensor:
+    """x*: bf16 NHWC [B,H,W,C*]; wt: bf16 [Cout, 3, 3, C0+C1]; out: [B,Ho,Wo,Cout] fp32|bf16."""
+    lib = _lib.load()
+    _chk(x0, torch.bfloat16, "x0")
+    _chk(wt, torch.bfloat16, "wt")
+    B, H, W, C0 = (int(s) for s in x0.shape)
+    C1 = 0
+    if x1 is not None:
+        _chk(x1, torch.bfloat16, "x1")
+        C1 = int(x1.shape[-1])
+    Cout = int(wt.shape[0])
+    if wt.numel() != Cout * 9 * (C0 + C1):
+        raise ValueError("conv3x3 weight shape mismatch")
+    ep = _epilogue(out, bias, rowbias, 0, residual)
+    rc = lib.af_conv3x3_bf16(x0.data_ptr(), C0, _p(x1), C1, wt.data_ptr(), B, H, W, Cout, stride, byref(ep), bn,
+                             _stream())
+    _lib.check(rc, "af_conv3x3_bf16")
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Tensor, *, B: int, heads: int, Nq: int,
+              Nk: int, d: int, ldq: int, ldk: int, ldvt: int, vt_stride: int,
+              key_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    for t, n in ((q, "q"), (k, "k"), (vt, "vt"), (out, "out")):
+        if t.dtype != torch.bfloat16 or not t.is_cuda:
+            raise ValueError(f"{n} must be a CUDA bf16 tensor")
+    if key_mask is not None:
+        _chk(key_mask, torch.uint8, "key_mask")
+    rc = lib.af_attention_bf16(q.data_ptr(), ldq, k.data_ptr(), ldk, vt.data_ptr(), ldvt, vt_stride, _p(key_mask),
+                               out.data_ptr(), B, heads, Nq, Nk, d, _stream())
+    _lib.check(rc, "af_attention_bf16")
+    return out
+
+
+def _gn_workspace(B: int, device) -> torch.Tensor:
+    key = (B, device)
+    ws = _gn_ws.get(key)
+    if ws is None:
+        n = _lib.load().af_groupnorm_workspace_bytes(B)
+        ws = torch.empty(n // 4, dtype=torch.float32, device=device)
+        _gn_ws[key] = ws
+    return ws
+
+
+def groupnorm_silu(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool,
+                   out: torch.Tensor, *, x1: Optional[torch.Tensor] = None, raw: Optional[torch.Tensor] = None,
+                   workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x*: fp32 NHWC [B, H, W, C*] (or [B, HW, C*]); out: bf16 [B, HW, C0+C1]."""
+    lib = _lib.load()
+    _chk(x0, torch.float32, "x0")
+    _chk(out, torch.bfloat16, "out")
+    B, C0 = int(x0.shape[0]), int(x0.shape[-1])
+    HW = x0.numel() // (B * C0)
+    C1 = 0
+    if x1 is not None:
+        _chk(x1, torch.float32, "x1")
+        C1 = int(x1.shape[-1])
+    if raw is not None:
+        _chk(raw, torch.bfloat16, "raw")
+    ws = workspace if workspace is not None else _gn_workspace(B, x0.device)
+    rc = lib.af_groupnorm_silu(x0.data_ptr(), C0, _p(x1), C1, B, HW, gamma.data_ptr(), beta.data_ptr(), float(eps),
+                               1 if silu else 0, out.data_ptr(), _p(raw), ws.data_ptr(), _stream())
+    _lib.check(rc, "af_groupnorm_silu")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(x, torch.float32, "x")
+    _chk(out, torch.bfloat16, "out")
+    C = int(x.shape[-1])
+    rc = lib.af_layernorm(x.data_ptr(), x.numel() // C, C, gamma.data_ptr(), beta.data_ptr(), float(eps),
+                          out.data_ptr(), _stream())
+    _lib.check(rc, "af_layernorm")
+    return out
+
+
+def conv_in(x_nchw: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out_nhwc: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(x_nchw, torch.float32, "x")
+    _chk(w, torch.float32, "w")
+    _chk(out_nhwc, torch.float32, "out")
+    B, Cin, H, W = (int(s) for s in x_nchw.shape)
+    rc = lib.af_conv_in(x_nchw.data_ptr(), w.data_ptr(), _p(bias), out_nhwc.data_ptr(), B, Cin, H, W, int(w.shape[0]),
+                        _stream())
+    _lib.check(rc, "af_conv_in")
+    return out_nhwc
+
+
+def conv_out(x_nhwc: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, out_nchw: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(x_nhwc, torch.bfloat16, "x")
+    _chk(w_packed, torch.float32, "w")
+    _chk(out_nchw, torch.float32, "out")
+    B, H, W, C = (int(s) for s in x_nhwc.shape)
+    rc = lib.af_conv_out(x_nhwc.data_ptr(), w_packed.data_ptr(), _p(bias), out_nchw.data_ptr(), B, H, W, C,
+                         int(w_packed.shape[0]), _stream())
+    _lib.check(rc, "af_conv_out")
+    return out_nchw
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(t, torch.float32, "t")
+    B = int(t.shape[0])
+    if out is None:
+        out = torch.empty(B, dim, dtype=torch.float32, device=t.device)
+    rc = lib.af_timestep_embedding(t.data_ptr(), out.data_ptr(), B, dim, _stream())
+    _lib.check(rc, "af_timestep_embedding")
+    return out
+
+
+def linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, *,
+                 silu_in=False, silu_out=False) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(x, torch.float32, "x")
+    _chk(w, torch.float32, "w")
+    _chk(out, torch.float32, "out")
+    M, K = int(x.shape[0]), int(x.shape[1])
+    N = int(w.shape[0])
+    rc = lib.af_linear_small(x.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), M, N, K, int(silu_in),
+                             int(silu_out), _stream())
+    _lib.check(rc, "af_linear_small")
+    return out
+
+
+def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(x, torch.float32, "x")
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    rc = lib.af_cast_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+    _lib.check(rc, "af_cast_bf16")
+    return out
+
+
+def upsample2x_cast(x_nhwc: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(x_nhwc, torch.float32, "x")
+    _chk(out, torch.bfloat16, "out")
+    B, H, W, C = (int(s) for s in x_nhwc.shape)
+    rc = lib.af_upsample2x_cast(x_nhwc.data_ptr(), out.data_ptr(), B, H, W, C, _stream())
+    _lib.check(rc, "af_upsample2x_cast")
+    return out
+
+
+def cfg_ddim_update(x: torch.Tensor, eps: torch.Tensor, coef_table: torch.Tensor, x_prev: torch.Tensor,
+                    pred_x0: Optional[torch.Tensor], *, has_uncond: bool, noise: Optional[torch.Tensor] = None,
+                    step_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(x, torch.float32, "x")
+    _chk(eps, torch.float32, "eps")
+    _chk(coef_table, torch.float32, "coef_table")
+    rc = lib.af_cfg_ddim_update(x.data_ptr(), eps.data_ptr(), int(has_uncond), _p(noise), coef_table.data_ptr(),
+                                _p(step_idx), x_prev.data_ptr(), _p(pred_x0), x.numel(), _stream())
+    _lib.check(rc, "af_cfg_ddim_update")
+    return x_prev
+
+
+def advance_step(step_idx: torch.Tensor, t_table: torch.Tensor, t_buf: torch.Tensor, num_steps: int) -> None:
+    lib = _lib.load()
+    rc = lib.af_advance_step(step_idx.data_ptr(), t_table.data_ptr(), t_buf.data_ptr(), int(t_buf.shape[0]),
+                             int(num_steps), _stream())
+    _lib.check(rc, "af_advance_step")

@@ -1,0 +1,310 @@
+"""Per-kernel parity on a B200: every af_* entry point against a plain PyTorch fp32 reference of the same
+op, on bf16-rounded operands (so only accumulation order / the documented bf16 roundings differ).
+All calls go through the C ABI (adaprompt_b200.ops -> ctypes -> libadaface_b200.so)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def _rand(*shape, seed=0, scale=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 128, 64, 0), (128, 64, 64, 64), (256, 320, 320, 0), (4096, 320, 320, 160), (1000, 640, 2560, 0),
+    (77 * 3, 1280, 768, 0), (8192, 2560, 320, 256), (300, 256, 1280, 128), (64, 768, 320, 128), (512, 1280, 5120, 0),
+])
+def test_gemm_plain(M, N, K, bn):
+    from adaprompt_b200 import ops
+    a = _rand(M, K, seed=1, dtype=torch.bfloat16)
+    w = _rand(N, K, seed=2, scale=K ** -0.5, dtype=torch.bfloat16)
+    bias = _rand(N, seed=3)
+    out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    ops.gemm(a, w, out, bias=bias, bn=bn)
+    ref = a.float() @ w.float().t() + bias
+    assert _rel(out, ref) < 2e-5
+    outb = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, w, outb, bias=bias, bn=bn)
+    assert _rel(outb, ref) < 4e-3
+
+
+def test_gemm_residual_rowbias_slice():
+    from adaprompt_b200 import ops
+    B, HW, N, K = 3, 256, 320, 640
+    M = B * HW
+    a = _rand(M, K, seed=1, dtype=torch.bfloat16)
+    w = _rand(N, K, seed=2, scale=K ** -0.5, dtype=torch.bfloat16)
+    bias = _rand(N, seed=3)
+    rowbias = _rand(B, N, seed=4)
+    res = _rand(M, N, seed=5)
+    out = torch.zeros(M, 2 * N, device=DEV, dtype=torch.float32)
+    ops.gemm(a, w, out[:, N:], bias=bias, rowbias=rowbias, rows_per_group=HW, residual=res, ldo=2 * N, ldr=N)
+    ref = a.float() @ w.float().t() + bias + rowbias.repeat_interleave(HW, 0) + res
+    assert _rel(out[:, N:], ref) < 2e-5
+    assert out[:, :N].abs().max().item() == 0.0
+
+
+def test_gemm_dual_source():
+    from adaprompt_b200 import ops
+    M, N, K0, K1 = 1024, 320, 640, 320
+    a0 = _rand(M, K0, seed=1, dtype=torch.bfloat16)
+    a1 = _rand(M, K1, seed=2, dtype=torch.bfloat16)
+    w = _rand(N, K0 + K1, seed=3, scale=(K0 + K1) ** -0.5, dtype=torch.bfloat16)
+    out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    ops.gemm(a0, w, out, a1=a1)
+    ref = torch.cat([a0, a1], 1).float() @ w.float().t()
+    assert _rel(out, ref) < 2e-5
+
+
+def test_gemm_geglu():
+    from adaprompt_b200 import ops
+    from adaprompt_b200.packing import pack_geglu
+    M, C = 1024, 320
+    x = _rand(M, C, seed=1, dtype=torch.bfloat16)
+    w = _rand(8 * C, C, seed=2, scale=C ** -0.5)      # nn.Linear(C, 8C): rows [value 4C | gate 4C]
+    b = _rand(8 * C, seed=3, scale=0.1)
+    wp, bp = pack_geglu(w, b)
+    out = torch.empty(M, 4 * C, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(x, wp.to(torch.bfloat16).contiguous(), out, bias=bp.contiguous(), geglu=True)
+    h = x.float() @ w.to(torch.bfloat16).float().t() + b
+    val, gate = h.chunk(2, dim=-1)
+    ref = val * F.gelu(gate)
+    assert _rel(out, ref) < 4e-3
+
+
+def test_gemm_swap_ab_transposed_out():
+    """V^T = Wv . X^T : the same kernel with the weight as the M operand."""
+    from adaprompt_b200 import ops
+    tokens, C, K = 2048, 320, 320
+    x = _rand(tokens, K, seed=1, dtype=torch.bfloat16)
+    wv = _rand(C, K, seed=2, scale=K ** -0.5, dtype=torch.bfloat16)
+    vt = torch.empty(C, tokens, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(wv, x, vt, bn=128)
+    ref = (x.float() @ wv.float().t()).t()
+    assert _rel(vt, ref) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ conv3x3
+def _conv_ref(x_nhwc, w_oihw, bias, stride):
+    y = F.conv2d(x_nhwc.float().permute(0, 3, 1, 2), w_oihw.float(), bias, stride=stride, padding=1)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [
+    (2, 64, 64, 320, 320, 1), (2, 32, 32, 640, 640, 1), (2, 16, 16, 1280, 1280, 1), (3, 8, 8, 1280, 1280, 1),
+    (1, 64, 64, 320, 320, 2), (2, 32, 32, 640, 640, 2), (3, 16, 16, 1280, 1280, 2),
+    (1, 96, 96, 320, 320, 1), (1, 24, 24, 640, 320, 1), (2, 12, 12, 1280, 640, 1),
+])
+def test_conv3x3(B, H, W, Cin, Cout, stride):
+    from adaprompt_b200 import ops
+    from adaprompt_b200.packing import pack_conv3x3
+    x = _rand(B, H, W, Cin, seed=1, dtype=torch.bfloat16)
+    w = _rand(Cout, Cin, 3, 3, seed=2, scale=(9 * Cin) ** -0.5).to(torch.bfloat16)
+    bias = _rand(Cout, seed=3)
+    Ho, Wo = H // stride, W // stride
+    out = torch.empty(B, Ho, Wo, Cout, device=DEV, dtype=torch.float32)
+    ops.conv3x3(x, pack_conv3x3(w), out, stride=stride, bias=bias)
+    ref = _conv_ref(x, w, bias, stride)
+    assert _rel(out, ref) < 2e-5
+
+
+def test_conv3x3_dual_source_rowbias_residual():
+    from adaprompt_b200 import ops
+    from adaprompt_b200.packing import pack_conv3x3
+    B, H, W, C0, C1, Cout = 2, 32, 32, 640, 320, 640
+    x0 = _rand(B, H, W, C0, seed=1, dtype=torch.bfloat16)
+    x1 = _rand(B, H, W, C1, seed=2, dtype=torch.bfloat16)
+    w = _rand(Cout, C0 + C1, 3, 3, seed=3, scale=(9 * (C0 + C1)) ** -0.5).to(torch.bfloat16)
+    bias = _rand(Cout, seed=4)
+    emb = _rand(B, Cout, seed=5)
+    res = _rand(B, H, W, Cout, seed=6)
+    out = torch.empty(B, H, W, Cout, device=DEV, dtype=torch.float32)
+    ops.conv3x3(x0, pack_conv3x3(w), out, x1=x1, bias=bias, rowbias=emb, residual=res)
+    ref = _conv_ref(torch.cat([x0, x1], -1), w, bias, 1) + emb[:, None, None, :] + res
+    assert _rel(out, ref) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_case(B, N, Nk, d, seed=0, mask=False, cross=False):
+    from adaprompt_b200 import ops
+    heads = 8
+    C = heads * d
+    dp = 48 if d == 40 else d
+    scale = d ** -0.5
+    q = _rand(B, N, heads, d, seed=seed + 1)
+    k = _rand(B, Nk, heads, d, seed=seed + 2)
+    v = _rand(B, Nk, heads, d, seed=seed + 3)
+    qs = (q * (scale * math.log2(math.e))).to(torch.bfloat16)
+    kb, vb = k.to(torch.bfloat16), v.to(torch.bfloat16)
+    qbuf = torch.zeros(B, N, heads, dp, device=DEV, dtype=torch.bfloat16)
+    kbuf = torch.zeros(B, Nk, heads, dp, device=DEV, dtype=torch.bfloat16)
+    qbuf[..., :d] = qs
+    kbuf[..., :d] = kb
+    nk_pad = ((Nk + 7) // 8) * 8 if cross else Nk
+    vt = torch.zeros(C, B * nk_pad, device=DEV, dtype=torch.bfloat16)
+    vt.view(C, B, nk_pad)[:, :, :Nk] = vb.permute(2, 3, 0, 1).reshape(C, B, Nk)
+    km = None
+    if mask:
+        g = torch.Generator().manual_seed(seed + 9)
+        km = (torch.rand(B, Nk, generator=g) > 0.3).to(torch.uint8).to(DEV)
+        km[:, 0] = 1
+    out = torch.empty(B, N, C, device=DEV, dtype=torch.bfloat16)
+    ops.attention(qbuf, kbuf, vt, out, B=B, heads=heads, Nq=N, Nk=Nk, d=d, ldq=heads * dp, ldk=heads * dp,
+                  ldvt=B * nk_pad, vt_stride=nk_pad, key_mask=km)
+    # reference: attention.py:198-242 on the same bf16-rounded operands (q carries scale*log2e -> use exp2)
+    s = torch.einsum("bihd,bjhd->bhij", qs.float(), kb.float())
+    if km is not None:
+        s = s.masked_fill(~km.bool()[:, None, None, :], float("-inf"))
+    p = torch.softmax(s * math.log(2.0), dim=-1)
+    ref = torch.einsum("bhij,bjhd->bihd", p, vb.float()).reshape(B, N, C)
+    return _rel(out, ref)
+
+
+@pytest.mark.parametrize("B,N,d", [(1, 4096, 40), (2, 1024, 80), (2, 256, 160), (3, 64, 160), (1, 2304, 80),
+                                   (2, 144, 160), (1, 576, 160)])
+def test_self_attention(B, N, d):
+    assert _attn_case(B, N, N, d) < 6e-3
+
+
+@pytest.mark.parametrize("B,N,d", [(2, 4096, 40), (2, 1024, 80), (2, 256, 160), (2, 64, 160)])
+def test_cross_attention_77(B, N, d):
+    assert _attn_case(B, N, 77, d, seed=5, cross=True) < 6e-3
+
+
+def test_self_attention_key_mask():
+    assert _attn_case(2, 1024, 1024, 80, seed=7, mask=True) < 6e-3
+
+
+# ------------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("B,HW,C0,C1,eps,silu", [
+    (2, 4096, 320, 0, 1e-5, True), (2, 1024, 640, 320, 1e-5, True), (3, 256, 1280, 640, 1e-5, True),
+    (2, 64, 1280, 1280, 1e-5, True), (2, 4096, 320, 0, 1e-6, False), (1, 1024, 640, 640, 1e-5, True),
+    (16, 64, 2560 - 1280, 1280, 1e-5, True),
+])
+def test_groupnorm_silu(B, HW, C0, C1, eps, silu):
+    from adaprompt_b200 import ops
+    x0 = _rand(B, HW, C0, seed=1) * 2 + 0.3
+    x1 = _rand(B, HW, C1, seed=2) - 0.5 if C1 else None
+    C = C0 + C1
+    gamma = 1 + 0.1 * _rand(C, seed=3)
+    beta = 0.1 * _rand(C, seed=4)
+    out = torch.empty(B, HW, C, device=DEV, dtype=torch.bfloat16)
+    raw = torch.empty(B, HW, C, device=DEV, dtype=torch.bfloat16)
+    ops.groupnorm_silu(x0, gamma, beta, eps, silu, out, x1=x1, raw=raw)
+    x = x0 if x1 is None else torch.cat([x0, x1], -1)
+    ref = F.group_norm(x.permute(0, 2, 1), 32, gamma, beta, eps).permute(0, 2, 1)
+    if silu:
+        ref = F.silu(ref)
+    assert _rel(out, ref) < 3e-3
+    assert (out.float() - ref).abs().max().item() < 0.05
+    assert torch.equal(raw, x.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("rows,C", [(4096, 320), (2048, 640), (512, 1280), (77, 768), (33, 1024)])
+def test_layernorm(rows, C):
+    from adaprompt_b200 import ops
+    x = _rand(rows, C, seed=1) * 1.7 + 0.2
+    gamma = 1 + 0.1 * _rand(C, seed=2)
+    beta = 0.1 * _rand(C, seed=3)
+    out = torch.empty(rows, C, device=DEV, dtype=torch.bfloat16)
+    ops.layernorm(x, gamma, beta, 1e-5, out)
+    ref = F.layer_norm(x, (C,), gamma, beta, 1e-5)
+    assert _rel(out, ref) < 3e-3
+
+
+# ------------------------------------------------------------------------------------------------ misc
+def test_conv_in_out():
+    from adaprompt_b200 import ops
+    B, H, W = 2, 64, 64
+    x = _rand(B, 4, H, W, seed=1)
+    w = _rand(320, 4, 3, 3, seed=2, scale=1 / 6.0)
+    b = _rand(320, seed=3, scale=0.1)
+    y = torch.empty(B, H, W, 320, device=DEV)
+    ops.conv_in(x, w, b, y)
+    ref = F.conv2d(x, w, b, padding=1).permute(0, 2, 3, 1)
+    assert _rel(y, ref) < 1e-5
+
+    xo = _rand(B, H, W, 320, seed=4, dtype=torch.bfloat16)
+    wo = _rand(4, 320, 3, 3, seed=5, scale=(9 * 320) ** -0.5)
+    bo = _rand(4, seed=6, scale=0.1)
+    yo = torch.empty(B, 4, H, W, device=DEV)
+    ops.conv_out(xo, wo.permute(0, 2, 3, 1).contiguous(), bo, yo)
+    refo = F.conv2d(xo.float().permute(0, 3, 1, 2), wo, bo, padding=1)
+    assert _rel(yo, refo) < 1e-5
+
+
+def test_time_embedding_and_small_linear():
+    from adaprompt_b200 import ops
+    t = torch.tensor([981.0, 501.0, 21.0, 1.0], device=DEV)
+    emb = ops.timestep_embedding(t, 320)
+    half = 160
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half).to(DEV)
+    args = t[:, None] * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    assert (emb - ref).abs().max().item() < 2e-4
+
+    x = _rand(5, 1280, seed=1)
+    w = _rand(640, 1280, seed=2, scale=1280 ** -0.5)
+    b = _rand(640, seed=3)
+    y = torch.empty(5, 640, device=DEV)
+    ops.linear_small(x, w, b, y, silu_in=True, silu_out=True)
+    ref = F.silu(F.silu(x) @ w.t() + b)
+    assert _rel(y, ref) < 1e-5
+
+
+def test_casts_and_upsample():
+    from adaprompt_b200 import ops
+    x = _rand(2, 8, 8, 64, seed=1)
+    assert torch.equal(ops.cast_bf16(x), x.to(torch.bfloat16))
+    up = torch.empty(2, 16, 16, 64, device=DEV, dtype=torch.bfloat16)
+    ops.upsample2x_cast(x, up)
+    ref = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(up, ref)
+
+
+def test_cfg_ddim_update_bit_exact():
+    """ddim.py:260,279,283,295 in the reference's fp32 operation order -> bit-exact vs torch."""
+    from adaprompt_b200 import ops
+    b = 3
+    x = _rand(b, 4, 64, 64, seed=1)
+    eps = _rand(2 * b, 4, 64, 64, seed=2)
+    a_t, a_prev, g = torch.tensor(0.3217), torch.tensor(0.3561), 3.6938775510204083
+    s1m = torch.sqrt(1 - a_t)
+    coef = torch.tensor([[g, s1m.item(), a_t.sqrt().item(), a_prev.sqrt().item(), (1. - a_prev - 0.0).sqrt().item(),
+                          0.0, 0, 0]], dtype=torch.float32, device=DEV)
+    xp = torch.empty_like(x)
+    p0 = torch.empty_like(x)
+    ops.cfg_ddim_update(x, eps, coef, xp, p0, has_uncond=True)
+    xc, ec = x.cpu(), eps.cpu()
+    e_t, e_u = ec.chunk(2)
+    e = e_u + g * (e_t - e_u)
+    a_t_f = torch.full((b, 1, 1, 1), a_t.item())
+    a_prev_f = torch.full((b, 1, 1, 1), a_prev.item())
+    sig = torch.full((b, 1, 1, 1), 0.0)
+    s1m_f = torch.full((b, 1, 1, 1), s1m.item())
+    pred = (xc - s1m_f * e) / a_t_f.sqrt()
+    dir_xt = (1. - a_prev_f - sig ** 2).sqrt() * e
+    ref = a_prev_f.sqrt() * pred + dir_xt + sig * torch.zeros_like(xc)
+    assert torch.equal(p0.cpu(), pred)
+    assert torch.equal(xp.cpu(), ref)
