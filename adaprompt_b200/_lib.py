@@ -22,6 +22,7 @@ class AfEpilogue(Structure):
         ("bias", c_void_p),
         ("rowbias", c_void_p),
         ("rows_per_group", c_int),
+        ("ld_rowbias", c_longlong),
         ("residual", c_void_p),
         ("ldr", c_longlong),
         ("out", c_void_p),

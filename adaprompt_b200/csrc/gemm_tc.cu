@@ -39,6 +39,7 @@ struct GemmParams {
   const float* bias;       // [N] or null
   const float* rowbias;    // [groups, N] or null; group = out_row / rows_per_group
   int rows_per_group;
+  long long ld_rowbias;
   const float* residual;   // [M, ldr] fp32 or null
   long long ldr;
   void* out;
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         grow = (static_cast<long long>(n) * p.H + h) * p.W + w;
       }
       const float* rb = nullptr;
-      if (p.rowbias && valid) rb = p.rowbias + (grow / p.rows_per_group) * static_cast<long long>(p.N);
+      if (p.rowbias && valid) rb = p.rowbias + (grow / p.rows_per_group) * p.ld_rowbias;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -355,6 +356,7 @@ static int fill_epilogue(GemmParams& p, const af_epilogue* ep, long long default
   p.bias = ep->bias;
   p.rowbias = ep->rowbias;
   p.rows_per_group = ep->rows_per_group > 0 ? ep->rows_per_group : 1;
+  p.ld_rowbias = ep->ld_rowbias > 0 ? ep->ld_rowbias : p.N;
   p.residual = ep->residual;
   p.ldr = ep->ldr > 0 ? ep->ldr : default_ldo;
   p.out = ep->out;
@@ -367,7 +369,7 @@ static int fill_epilogue(GemmParams& p, const af_epilogue* ep, long long default
   AF_CHECK_ARG(!ep->geglu || ep->out_dtype == AF_DTYPE_BF16, "geglu epilogue writes bf16 only");
   AF_CHECK_ARG(!ep->geglu || (!ep->residual && !ep->rowbias), "geglu epilogue: residual / rowbias unsupported");
   AF_CHECK_ARG((reinterpret_cast<uintptr_t>(ep->out) & 15) == 0, "epilogue: out not 16B aligned");
-  AF_CHECK_ARG(p.ldo % 8 == 0 && p.ldr % 4 == 0, "epilogue: ldo %lld / ldr %lld misaligned", p.ldo, p.ldr);
+  AF_CHECK_ARG(p.ldo % 8 == 0 && p.ldr % 4 == 0 && p.ld_rowbias % 4 == 0, "epilogue: ldo %lld / ldr %lld / ld_rowbias %lld misaligned", p.ldo, p.ldr, p.ld_rowbias);
   return 0;
 }
 

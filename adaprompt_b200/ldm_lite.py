@@ -1,0 +1,80 @@
+"""Adapter slice of ldm/models/diffusion/ddpm.py that sits between the sampler and the UNet:
+register_schedule :240-292, q_sample :416-419, apply_model :2192-2297 (live line :2292) and
+DiffusionWrapper.forward :5514-5544 (crossattn branch).  Everything else in ddpm.py (the Lightning
+training module, losses, optimisers) is out of scope."""
+from __future__ import annotations
+
+from functools import partial
+
+import numpy as np
+import torch
+from torch import nn
+
+from .diffusion_util import make_beta_schedule
+from .unet import UNetModel
+
+SD15_UNET_CONFIG = dict(  # configs/stable-diffusion/v1-inference-ada.yaml:35-51
+    image_size=32, in_channels=4, out_channels=4, model_channels=320, attention_resolutions=[4, 2, 1],
+    num_res_blocks=2, channel_mult=[1, 2, 4, 4], num_heads=8, use_spatial_transformer=True,
+    transformer_depth=1, context_dim=768, use_checkpoint=True, legacy=False)
+
+
+class DiffusionWrapper(nn.Module):
+    """ddpm.py:5505-5544: unpacks the (c_static_emb, c_in, extra_info) conditioning tuple."""
+
+    def __init__(self, diffusion_model: nn.Module, conditioning_key="crossattn"):
+        super().__init__()
+        self.diffusion_model = diffusion_model
+        self.conditioning_key = conditioning_key
+        assert conditioning_key == "crossattn", "only the crossattn branch is used by AdaFace"
+
+    def forward(self, x, t, c_concat=None, c_crossattn=None):
+        c_static_emb, c_in, extra_info = c_crossattn[0]                         # :5522-5524
+        return self.diffusion_model(x, t, context=c_static_emb, context_in=c_in, extra_info=extra_info)  # :5533
+
+
+class LatentDiffusionLite(nn.Module):
+    """What DDIMSampler needs from LatentDiffusion: betas / alphas_cumprod(_prev) / num_timesteps / device /
+    apply_model / q_sample, with the SD-1.5 'linear' schedule (v1-inference-ada.yaml:5-9)."""
+
+    def __init__(self, unet: nn.Module = None, timesteps=1000, linear_start=0.00085, linear_end=0.012,
+                 beta_schedule="linear", scale_factor=0.18215, parameterization="eps"):
+        super().__init__()
+        self.model = DiffusionWrapper(unet if unet is not None else UNetModel(**SD15_UNET_CONFIG))
+        self.parameterization = parameterization
+        self.scale_factor = scale_factor
+        self.register_schedule(beta_schedule, timesteps, linear_start, linear_end)
+
+    def register_schedule(self, beta_schedule, timesteps, linear_start, linear_end, cosine_s=8e-3):
+        """ddpm.py:240-292 (the buffers the sampling path reads)."""
+        betas = make_beta_schedule(beta_schedule, timesteps, linear_start=linear_start, linear_end=linear_end,
+                                   cosine_s=cosine_s)
+        alphas = 1. - betas
+        alphas_cumprod = np.cumprod(alphas, axis=0)
+        alphas_cumprod_prev = np.append(1., alphas_cumprod[:-1])
+        self.num_timesteps = int(betas.shape[0])
+        to_torch = partial(torch.tensor, dtype=torch.float32)
+        self.register_buffer("betas", to_torch(betas))
+        self.register_buffer("alphas_cumprod", to_torch(alphas_cumprod))
+        self.register_buffer("alphas_cumprod_prev", to_torch(alphas_cumprod_prev))
+        self.register_buffer("sqrt_alphas_cumprod", to_torch(np.sqrt(alphas_cumprod)))
+        self.register_buffer("sqrt_one_minus_alphas_cumprod", to_torch(np.sqrt(1. - alphas_cumprod)))
+
+    @property
+    def device(self):
+        return self.betas.device
+
+    def q_sample(self, x_start, t, noise=None):
+        """ddpm.py:416-419."""
+        noise = torch.randn_like(x_start) if noise is None else noise
+        a = self.sqrt_alphas_cumprod[t].reshape(-1, *((1,) * (x_start.dim() - 1)))
+        b = self.sqrt_one_minus_alphas_cumprod[t].reshape(-1, *((1,) * (x_start.dim() - 1)))
+        return a * x_start + b * noise
+
+    def apply_model(self, x_noisy, t, cond, return_ids=False):
+        """ddpm.py:2192-2201,2292."""
+        if not isinstance(cond, dict):
+            if not isinstance(cond, list):
+                cond = [cond]
+            cond = {"c_crossattn": cond}
+        return self.model(x_noisy, t, **cond)

@@ -36,16 +36,19 @@ def _chk(t: torch.Tensor, dtype, name: str) -> None:
 
 def _epilogue(out: torch.Tensor, bias=None, rowbias=None, rows_per_group=0, residual=None, geglu=False,
               ldo: int = 0, ldr: int = 0) -> AfEpilogue:
+    # rowbias may be a column slice of a wider [groups, total] matrix: its row stride is passed along
     ep = AfEpilogue()
     if bias is not None:
         _chk(bias, torch.float32, "bias")
     if rowbias is not None:
-        _chk(rowbias, torch.float32, "rowbias")
+        if rowbias.dtype != torch.float32 or not rowbias.is_cuda or rowbias.stride(-1) != 1:
+            raise ValueError("rowbias must be a CUDA fp32 tensor with unit column stride")
     if residual is not None:
         _chk(residual, torch.float32, "residual")
     ep.bias = _p(bias)
     ep.rowbias = _p(rowbias)
     ep.rows_per_group = int(rows_per_group)
+    ep.ld_rowbias = int(rowbias.stride(0)) if rowbias is not None and rowbias.dim() == 2 else 0
     ep.residual = _p(residual)
     ep.ldr = int(ldr)
     ep.out = out.data_ptr()

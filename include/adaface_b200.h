@@ -44,6 +44,7 @@ typedef struct af_epilogue {
   const float* bias;      /* [N] or NULL (nn.Linear / nn.Conv2d bias) */
   const float* rowbias;   /* [groups, N] or NULL: per-sample time-embedding add, openaimodel.py:268-277 */
   int rows_per_group;     /* rows sharing one rowbias row (H*W); <= 0: derived for conv */
+  long long ld_rowbias;   /* row pitch of rowbias in floats; <= 0: N */
   const float* residual;  /* [M, ldr] fp32 or NULL: residual adds attention.py:277,281,283,341 / openaimodel.py:279 */
   long long ldr;          /* <= 0: same as ldo */
   void* out;              /* [M, ldo] */

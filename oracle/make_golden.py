@@ -1,0 +1,101 @@
+"""TEST INFRASTRUCTURE - generates tests/golden/*.pt by running the UNMODIFIED reference modules
+(/root/reference, build container only) on the synthetic-weight recipe.  Run:
+
+    python oracle/make_golden.py [--skip-ddim]
+
+Every fixture stores the seeds needed to regenerate its inputs, checksums of those inputs, and the
+reference outputs.  tests/test_oracle_golden.py checks the oracle restatement against them (CPU),
+tests/test_unet_gpu.py checks the CUDA path against them (B200).
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as rh  # noqa: E402
+from oracle.golden_inputs import EXTRA_INFO, ddim_inputs, module_inputs, unet_inputs, checksum  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def main():
+    torch.set_num_threads(os.cpu_count() or 8)
+    os.makedirs(OUT, exist_ok=True)
+    ns = rh.import_reference()
+    unet = rh.build_ref_unet(seed=1234)
+    sd = unet.state_dict()
+
+    only = [a.split("=")[1] for a in sys.argv if a.startswith("--only=")]
+    # ---- 1. whole-UNet eps -----------------------------------------------------------------------
+    cases = {}
+    for name in () if (only and "unet" not in only) else ("b1_t501_64", "b2_t981_21_64", "b2_t501_32", "b1_t261_mask_32"):
+        x, t, ctx, extra = unet_inputs(name)
+        t0 = time.time()
+        with torch.no_grad():
+            eps = unet(x, t, context=ctx, extra_info=extra)
+        cases[name] = {"eps": eps.clone(), "x_sum": checksum(x), "ctx_sum": checksum(ctx)}
+        print(f"unet {name}: {time.time() - t0:.1f}s  |eps|={eps.abs().mean():.4f}")
+    if cases:
+        torch.save(cases, os.path.join(OUT, "unet_eps.pt"))
+
+    # ---- 2. module-level ---------------------------------------------------------------------------
+    mods = {}
+    mi = module_inputs()
+    with torch.no_grad():
+      if not only or "modules" in only:
+            rb = unet.output_blocks[5][0]           # ResBlock 1920 -> 1280 with 1x1 skip conv
+            mods["res_out5"] = rb(mi["res_out5"]["x"], mi["res_out5"]["emb"])
+            rb2 = unet.input_blocks[1][0]           # ResBlock 320 -> 320 identity skip
+            mods["res_in1"] = rb2(mi["res_in1"]["x"], mi["res_in1"]["emb"])
+            st = unet.input_blocks[4][1]            # SpatialTransformer C=640, d=80
+            c = mi["st_in4"]["ctx"]
+            mods["st_in4"] = st(mi["st_in4"]["x"], lambda: ((c, c), None), mask=None)
+            mods["st_in4_mask"] = st(mi["st_in4"]["x"], lambda: ((c, c), None), mask=mi["st_in4"]["mask"])
+            st1 = unet.input_blocks[1][1]           # C=320, d=40
+            c1 = mi["st_in1"]["ctx"]
+            mods["st_in1"] = st1(mi["st_in1"]["x"], lambda: ((c1, c1), None), mask=None)
+            stm = unet.middle_block[1]              # C=1280, d=160
+            cm = mi["st_mid"]["ctx"]
+            mods["st_mid"] = stm(mi["st_mid"]["x"], lambda: ((cm, cm), None), mask=None)
+            ca = st.transformer_blocks[0].attn1
+            mods["ca_self_in4"] = ca(mi["ca_in4"]["x"])
+            ca2 = st.transformer_blocks[0].attn2
+            mods["ca_cross_in4"] = ca2(mi["ca_in4"]["x"], context=mi["ca_in4"]["ctx"])
+            mods["ff_in4"] = st.transformer_blocks[0].ff(mi["ca_in4"]["x"])
+            mods["down_in3"] = unet.input_blocks[3][0](mi["down_in3"]["x"])
+            mods["up_out2"] = unet.output_blocks[2][1](mi["up_out2"]["x"])
+            mods["temb"] = ns.dutil.timestep_embedding(torch.tensor([981, 501, 21, 1]), 320)
+    if mods:
+        torch.save({k: v.clone() for k, v in mods.items()}, os.path.join(OUT, "modules.pt"))
+    print("modules done")
+
+    if "--skip-ddim" in sys.argv or (only and "ddim" not in only):
+        return
+    # ---- 3. DDIM trajectories ----------------------------------------------------------------------
+    traj = {}
+    for name in ("s10_32_g4_1", "s50_64_g4_1"):
+        S, shape, cond, uncond, gs, x_T = ddim_inputs(name)
+        model = rh.FakeLatentDiffusion(unet)
+        sampler = rh.cpu_ddim_sampler(model)
+        t0 = time.time()
+        with contextlib.redirect_stdout(io.StringIO()), torch.no_grad():
+            samples, inter = sampler.sample(S, shape[0], list(shape[1:]), conditioning=cond,
+                                            unconditional_conditioning=uncond, guidance_scale=gs, eta=0.0,
+                                            x_T=x_T, verbose=False, log_every_t=max(1, S // 10))
+        traj[name] = {"samples": samples.clone(), "x_inter": [t.clone() for t in inter["x_inter"]],
+                      "pred_x0": [t.clone() for t in inter["pred_x0"]], "calls": model.calls,
+                      "xT_sum": checksum(x_T)}
+        print(f"ddim {name}: {time.time() - t0:.1f}s, {model.calls} UNet calls")
+        torch.save(traj, os.path.join(OUT, "ddim_traj.pt"))
+
+
+if __name__ == "__main__":
+    main()

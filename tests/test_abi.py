@@ -1,0 +1,92 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads without a GPU and exports every symbol
+include/adaface_b200.h declares; the Python binding table mirrors the header; the host modules keep the
+reference's state_dict key names; and the product path refuses to run without CUDA (no CPU fallback)."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "adaface_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(af_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = _declared()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in adaface_b200.h but not exported"
+
+
+def test_binding_table_matches_header():
+    from adaprompt_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared()
+
+
+def test_version_and_error_string(lib):
+    assert lib.af_version() == 100
+    assert isinstance(lib.af_last_error(), bytes)
+
+
+def test_bad_arguments_are_rejected_without_a_gpu(lib):
+    """Argument validation happens before any CUDA call: negative rc + message."""
+    from ctypes import byref
+    from adaprompt_b200._lib import AfEpilogue
+    ep = AfEpilogue()
+    rc = lib.af_gemm_bf16(None, 0, 0, None, 0, 0, None, 0, 0, byref(ep), 0, None)
+    assert rc < 0 and b"null" in lib.af_last_error()
+    rc = lib.af_attention_bf16(1, 8, 1, 8, 1, 8, 8, None, 1, 1, 8, 8, 8, 64, None)
+    assert rc < 0 and b"head dim" in lib.af_last_error()
+    rc = lib.af_layernorm(1, 4, 30, 1, 1, 1e-5, 1, None)
+    assert rc < 0
+
+
+def test_state_dict_keys_match_reference_names():
+    from adaprompt_b200.ldm_lite import SD15_UNET_CONFIG
+    from adaprompt_b200.unet import UNetModel
+    from oracle.unet_oracle import UNetSpec
+    with torch.device("meta"):
+        m = UNetModel(**SD15_UNET_CONFIG)
+    sd = m.state_dict()
+    spec = UNetSpec().state_spec()   # pinned against the reference's own state_dict in oracle/make_golden.py
+    assert list(sd.keys()) == list(spec.keys())
+    assert all(tuple(sd[k].shape) == spec[k] for k in spec)
+    assert sum(v.numel() for v in sd.values()) == 859_520_964   # 859.52 M parameters
+    for k in ("input_blocks.1.1.transformer_blocks.0.attn1.to_q.weight", "middle_block.1.proj_out.weight",
+              "output_blocks.11.0.skip_connection.weight", "input_blocks.3.0.op.weight",
+              "output_blocks.2.1.conv.weight", "time_embed.2.bias", "out.2.weight",
+              "input_blocks.4.1.transformer_blocks.0.ff.net.0.proj.weight"):
+        assert k in sd
+
+
+def test_no_cpu_fallback():
+    from adaprompt_b200.unet import ResBlock
+    from adaprompt_b200 import ops
+    rb = ResBlock(320, 1280, 0.0, out_channels=320)
+    with pytest.raises(RuntimeError):
+        rb(torch.randn(1, 320, 8, 8), torch.randn(1, 1280))
+    with pytest.raises(ValueError):
+        ops.cast_bf16(torch.randn(8))
+
+
+def test_unsupported_configs_raise():
+    from adaprompt_b200.unet import ResBlock, UNetModel
+    with pytest.raises(NotImplementedError):
+        ResBlock(320, 1280, 0.0, use_scale_shift_norm=True)
+    with pytest.raises(NotImplementedError):
+        UNetModel(32, 4, 320, 4, 2, [4, 2, 1], num_heads=8, use_spatial_transformer=False)
+
+
+def test_weight_recipe_is_deterministic():
+    from adaprompt_b200.weights import synth_state_dict
+    spec = {"a.weight": (8, 4, 3, 3), "a.bias": (8,), "n.weight": (8,), "n.bias": (8,)}
+    s1, s2 = synth_state_dict(spec, 7), synth_state_dict(spec, 7)
+    assert all(torch.equal(s1[k], s2[k]) for k in spec)
+    assert not torch.equal(s1["a.weight"], synth_state_dict(spec, 8)["a.weight"])
+    assert s1["a.weight"].abs().max() <= 1 / 6.0 + 1e-6 and abs(s1["n.weight"].mean() - 1) < 0.1

@@ -1,0 +1,115 @@
+"""CPU checks of the host-side mirror logic that needs no kernel: DDIM schedule / coefficient rows of the
+product sampler against the oracle restatement, flag side channel, K/V cache keying."""
+import numpy as np
+import pytest
+import torch
+
+
+class _FakeModel:
+    """Schedule-only stand-in (no UNet) so DDIMSampler.make_schedule can run on CPU."""
+
+    def __init__(self):
+        from adaprompt_b200.ldm_lite import LatentDiffusionLite
+        lite = LatentDiffusionLite.__new__(LatentDiffusionLite)
+        torch.nn.Module.__init__(lite)
+        lite.register_schedule("linear", 1000, 0.00085, 0.012)
+        self.__dict__.update(betas=lite.betas, alphas_cumprod=lite.alphas_cumprod,
+                             alphas_cumprod_prev=lite.alphas_cumprod_prev, num_timesteps=1000,
+                             device=torch.device("cpu"),
+                             sqrt_one_minus_alphas_cumprod=lite.sqrt_one_minus_alphas_cumprod)
+
+
+def _cpu_sampler():
+    from adaprompt_b200.ddim import DDIMSampler
+
+    class S(DDIMSampler):
+        def register_buffer(self, name, attr):   # the reference forces cuda here (ddim.py:22-26)
+            setattr(self, name, attr)
+
+    return S(_FakeModel())
+
+
+def test_schedule_matches_oracle():
+    from oracle.unet_oracle import ddim_schedule, make_alphas_cumprod
+    s = _cpu_sampler()
+    s.make_schedule(50, ddim_eta=0.0, verbose=False)
+    ts, alphas, alphas_prev, sigmas, s1m = ddim_schedule(50)
+    assert np.array_equal(s.ddim_timesteps, ts)
+    assert torch.equal(s.ddim_alphas, alphas)
+    assert np.array_equal(np.asarray(s.ddim_alphas_prev), np.asarray(alphas_prev))
+    assert torch.equal(torch.as_tensor(s.ddim_sqrt_one_minus_alphas), torch.as_tensor(s1m))
+    ac = torch.tensor(make_alphas_cumprod(), dtype=torch.float32)
+    assert torch.equal(s.alphas_cumprod, ac)
+
+
+def test_coef_rows_match_reference_scalar_ops():
+    """Row = the fp32 scalars p_sample_ddim builds with torch.full (ddim.py:273-283)."""
+    from oracle.unet_oracle import ddim_schedule, guidance_schedule
+    s = _cpu_sampler()
+    s.make_schedule(50, ddim_eta=0.0, verbose=False)
+    ts, alphas, alphas_prev, sigmas, s1m = ddim_schedule(50)
+    gs = guidance_schedule(50, (4.0, 1.0))
+    for i in (0, 7, 49):
+        index = 50 - i - 1
+        row = s._coef_row(index, gs[i])
+        a_t = torch.full((1,), alphas[index])
+        a_prev = torch.full((1,), alphas_prev[index])
+        sig = torch.full((1,), sigmas[index])
+        assert row[0] == float(torch.tensor(gs[i], dtype=torch.float32))
+        assert row[1] == float(torch.full((1,), s1m[index]))
+        assert row[2] == float(a_t.sqrt()) and row[3] == float(a_prev.sqrt())
+        assert row[4] == float((1. - a_prev - sig ** 2).sqrt()) and row[5] == 0.0
+
+
+def test_set_cross_attn_flags_roundtrip():
+    """openaimodel.py:723-824: layerwise flags land on attn2 of the 16 CA layers and are restorable."""
+    from adaprompt_b200.ldm_lite import SD15_UNET_CONFIG
+    from adaprompt_b200.unet import ALL_CA_LAYER_INDICES, UNetModel
+    with torch.device("meta"):
+        m = UNetModel(**SD15_UNET_CONFIG)
+    sizes = np.arange(16)
+    old, _ = m.set_cross_attn_flags(ca_flag_dict={"use_conv_attn_kernel_size:layerwise": sizes, "is_training": False})
+    mods = m._layer_modules()
+    assert len(mods) == 25
+    for ca_idx, layer_idx in enumerate(ALL_CA_LAYER_INDICES):
+        attn2 = mods[layer_idx][1].transformer_blocks[0].attn2
+        assert attn2.use_conv_attn_kernel_size == ca_idx and attn2.is_training is False
+    assert old == {"use_conv_attn_kernel_size:layerwise": [-1] * 16, "is_training": True}
+    m.set_cross_attn_flags(ca_flag_dict=old)
+    assert mods[1][1].transformer_blocks[0].attn2.use_conv_attn_kernel_size == -1
+    old2, _ = m.set_cross_attn_flags(ca_flag_dict={"save_attn_vars": True}, ca_layer_indices=[7, 8, 12])
+    assert mods[7][1].transformer_blocks[0].attn2.save_attn_vars and not mods[1][1].transformer_blocks[0].attn2.save_attn_vars
+    m.set_cross_attn_flags(ca_flag_dict=old2, ca_layer_indices=[7, 8, 12])
+    assert m.set_cross_attn_flags() == (None, None)
+
+
+def test_unet_block_layout_matches_survey():
+    """22 ResBlocks, 16 SpatialTransformers, 3 Downsample, 3 Upsample; head dims 40/80/160."""
+    from adaprompt_b200.attention import SpatialTransformer
+    from adaprompt_b200.ldm_lite import SD15_UNET_CONFIG
+    from adaprompt_b200.unet import Downsample, ResBlock, UNetModel, Upsample
+    with torch.device("meta"):
+        m = UNetModel(**SD15_UNET_CONFIG)
+    count = lambda t: sum(isinstance(x, t) for x in m.modules())
+    assert (count(ResBlock), count(SpatialTransformer), count(Downsample), count(Upsample)) == (22, 16, 3, 3)
+    mods = m._layer_modules()
+    heads = {i: mods[i][1].transformer_blocks[0].attn1.dim_head for i in m._ca_modules()}
+    assert all(heads[i] == 40 for i in (1, 2, 22, 23, 24))
+    assert all(heads[i] == 80 for i in (4, 5, 19, 20, 21))
+    assert all(heads[i] == 160 for i in (7, 8, 12, 16, 17, 18))
+
+
+def test_packing_layouts():
+    from adaprompt_b200.packing import pack_conv3x3, pack_geglu, pack_qk
+    w = torch.arange(2 * 3 * 9, dtype=torch.float32).reshape(2, 3, 3, 3)
+    p = pack_conv3x3(w)
+    assert p.shape == (2, 3, 3, 3) and float(p[1, 2, 0, 1]) == float(w[1, 1, 2, 0])
+    wg = torch.arange(512 * 2, dtype=torch.float32).reshape(512, 2)
+    bg = torch.arange(512, dtype=torch.float32)
+    wp, bp = pack_geglu(wg, bg)
+    assert torch.equal(bp[:128], bg[:128]) and torch.equal(bp[128:256], bg[256:384]) and torch.equal(bp[256:384], bg[128:256])
+    assert torch.equal(wp[128:256], wg[256:384])
+    wq = torch.randn(320, 320)
+    pq = pack_qk(wq, wq, 8)
+    assert pq.shape == (2 * 8 * 48, 320)
+    assert float(pq.view(2, 8, 48, 320)[:, :, 40:].abs().max()) == 0.0   # zero pad rows -> zero pad columns

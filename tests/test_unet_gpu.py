@@ -1,0 +1,159 @@
+"""Parity of the CUDA path (through the reference-shaped module API -> C ABI) against
+  (1) golden vectors produced by the unmodified reference modules (tests/golden, oracle/make_golden.py),
+  (2) the CPU oracle (oracle/unet_oracle.py) on freshly seeded inputs.
+Tolerances are the north-star ones: per-step eps <= 1e-2 relative L2 (bf16 operands vs fp32 reference),
+final latents after the DDIM loop <= 2e-2 relative L2."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+EPS_TOL = 1e-2
+DDIM_TOL = 2e-2
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+@pytest.fixture(scope="module")
+def unet():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from adaprompt_b200.ldm_lite import SD15_UNET_CONFIG
+    from adaprompt_b200.unet import UNetModel
+    from adaprompt_b200.weights import spec_of, synth_state_dict
+    with torch.device("meta"):
+        m = UNetModel(**SD15_UNET_CONFIG)
+    m = m.to_empty(device="cuda")
+    sd = synth_state_dict(spec_of(m), 1234)
+    m.load_state_dict(sd)
+    m.eval()
+    return m
+
+
+@pytest.fixture(scope="module")
+def state_dict():
+    from adaprompt_b200.weights import synth_state_dict
+    from oracle.unet_oracle import UNetSpec
+    return synth_state_dict(UNetSpec().state_spec(), 1234)
+
+
+def _cuda_extra(extra):
+    return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in extra.items()}
+
+
+@pytest.mark.parametrize("name", ["b2_t501_32", "b1_t261_mask_32", "b1_t501_64", "b2_t981_21_64"])
+def test_unet_eps_vs_reference_golden(unet, name):
+    from oracle.golden_inputs import checksum, unet_inputs
+    gold = torch.load(os.path.join(GOLD, "unet_eps.pt"))[name]
+    x, t, ctx, extra = unet_inputs(name)
+    assert abs(checksum(x) - gold["x_sum"]) < 1e-6 * gold["x_sum"]
+    assert abs(checksum(ctx) - gold["ctx_sum"]) < 1e-6 * gold["ctx_sum"]
+    with torch.no_grad():
+        eps = unet(x.cuda(), t.cuda(), context=ctx.cuda(), extra_info=_cuda_extra(extra))
+    err = _rel(eps, gold["eps"])
+    print(f"unet eps {name}: rel-L2 {err:.3e}")
+    assert err < EPS_TOL
+
+
+def test_unet_eps_vs_oracle_fresh_inputs(unet, state_dict):
+    """Oracle computed here on the box's CPU (16x16 latent keeps it to ~1 s)."""
+    from oracle.golden_inputs import EXTRA_INFO
+    from oracle.unet_oracle import UNetSpec, unet_forward
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(2, 4, 16, 16, generator=g)
+    t = torch.tensor([741, 101])
+    ctx = torch.randn(32, 77, 768, generator=g)
+    with torch.no_grad():
+        ref = unet_forward(state_dict, UNetSpec(), x, t, ctx, dict(EXTRA_INFO))
+        eps = unet(x.cuda(), t.cuda(), context=ctx.cuda(), extra_info=dict(EXTRA_INFO))
+    assert _rel(eps, ref) < EPS_TOL
+
+
+def test_modules_vs_reference_golden(unet):
+    from oracle.golden_inputs import module_inputs
+    gold = torch.load(os.path.join(GOLD, "modules.pt"))
+    mi = {k: {kk: vv.cuda() for kk, vv in v.items()} for k, v in module_inputs().items()}
+    errs = {}
+    with torch.no_grad():
+        errs["res_out5"] = _rel(unet.output_blocks[5][0](mi["res_out5"]["x"], mi["res_out5"]["emb"]), gold["res_out5"])
+        errs["res_in1"] = _rel(unet.input_blocks[1][0](mi["res_in1"]["x"], mi["res_in1"]["emb"]), gold["res_in1"])
+        st = unet.input_blocks[4][1]
+        c = mi["st_in4"]["ctx"]
+        errs["st_in4"] = _rel(st(mi["st_in4"]["x"], lambda: ((c, c), None), mask=None), gold["st_in4"])
+        errs["st_in4_mask"] = _rel(st(mi["st_in4"]["x"], lambda: ((c, c), None), mask=mi["st_in4"]["mask"]),
+                                   gold["st_in4_mask"])
+        c1 = mi["st_in1"]["ctx"]
+        errs["st_in1"] = _rel(unet.input_blocks[1][1](mi["st_in1"]["x"], lambda: ((c1, c1), None)), gold["st_in1"])
+        cm = mi["st_mid"]["ctx"]
+        errs["st_mid"] = _rel(unet.middle_block[1](mi["st_mid"]["x"], lambda: ((cm, cm), None)), gold["st_mid"])
+        tb = st.transformer_blocks[0]
+        errs["ca_self_in4"] = _rel(tb.attn1(mi["ca_in4"]["x"]), gold["ca_self_in4"])
+        errs["ca_cross_in4"] = _rel(tb.attn2(mi["ca_in4"]["x"], context=mi["ca_in4"]["ctx"]), gold["ca_cross_in4"])
+        errs["ff_in4"] = _rel(tb.ff(mi["ca_in4"]["x"]), gold["ff_in4"])
+        errs["down_in3"] = _rel(unet.input_blocks[3][0](mi["down_in3"]["x"]), gold["down_in3"])
+        errs["up_out2"] = _rel(unet.output_blocks[2][1](mi["up_out2"]["x"]), gold["up_out2"])
+    print({k: f"{v:.2e}" for k, v in errs.items()})
+    for k, v in errs.items():
+        assert v < EPS_TOL, (k, v)
+
+
+def _sampler(unet, graph):
+    from adaprompt_b200.ddim import DDIMSampler
+    from adaprompt_b200.ldm_lite import LatentDiffusionLite
+    model = LatentDiffusionLite(unet).cuda()
+    return DDIMSampler(model, use_cuda_graph=graph)
+
+
+def _run_ddim(unet, name, graph):
+    from oracle.golden_inputs import ddim_inputs
+    S, shape, cond, uncond, gs, x_T = ddim_inputs(name)
+    cond = (cond[0].cuda(), cond[1], cond[2])
+    uncond = (uncond[0].cuda(), uncond[1], uncond[2])
+    sampler = _sampler(unet, graph)
+    samples, inter = sampler.sample(S, shape[0], list(shape[1:]), conditioning=cond,
+                                    unconditional_conditioning=uncond, guidance_scale=gs, eta=0.0,
+                                    x_T=x_T.cuda(), verbose=False, log_every_t=max(1, S // 10))
+    return samples, inter
+
+
+@pytest.mark.parametrize("name", ["s10_32_g4_1", "s50_64_g4_1"])
+def test_ddim_trajectory_vs_reference_golden(unet, name):
+    gold = torch.load(os.path.join(GOLD, "ddim_traj.pt"))[name]
+    samples, inter = _run_ddim(unet, name, graph=True)
+    errs = [_rel(a, b) for a, b in zip(inter["x_inter"][1:], gold["x_inter"][1:])]
+    print(f"ddim {name}: per-checkpoint rel-L2 {['%.2e' % e for e in errs]}, final {_rel(samples, gold['samples']):.3e}")
+    assert len(inter["x_inter"]) == len(gold["x_inter"])
+    assert _rel(samples, gold["samples"]) < DDIM_TOL
+    assert max(errs) < DDIM_TOL
+
+
+def test_ddim_graph_replay_equals_eager(unet):
+    """The captured-graph loop and the per-step eager loop launch the same kernels: bit-identical."""
+    s_g, i_g = _run_ddim(unet, "s10_32_g4_1", graph=True)
+    s_e, i_e = _run_ddim(unet, "s10_32_g4_1", graph=False)
+    assert torch.equal(s_g, s_e)
+    assert all(torch.equal(a, b) for a, b in zip(i_g["pred_x0"][1:], i_e["pred_x0"][1:]))
+
+
+def test_guidance_scale_must_be_tuple(unet):
+    from oracle.golden_inputs import ddim_inputs
+    S, shape, cond, uncond, gs, x_T = ddim_inputs("s10_32_g4_1")
+    sampler = _sampler(unet, True)
+    with pytest.raises(UnboundLocalError):
+        sampler.sample(S, 1, list(shape[1:]), conditioning=(cond[0].cuda(), cond[1], cond[2]), guidance_scale=4.0,
+                       unconditional_conditioning=(uncond[0].cuda(), uncond[1], uncond[2]), x_T=x_T.cuda(),
+                       verbose=False)
+
+
+def test_no_cpu_fallback():
+    from adaprompt_b200.ldm_lite import SD15_UNET_CONFIG
+    from adaprompt_b200.unet import ResBlock
+    rb = ResBlock(320, 1280, 0.0, out_channels=320)
+    with pytest.raises(RuntimeError):
+        rb(torch.randn(1, 320, 8, 8), torch.randn(1, 1280))
