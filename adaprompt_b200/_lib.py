@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import types
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -65,7 +66,7 @@ class AdaFaceB200Error(RuntimeError):
     pass
 
 
-def load() -> ctypes.CDLL:
+def load():
     """Loads the shared library (building is the job of __graft_entry__.build / adaprompt_b200.build)."""
     global _lib
     if _lib is not None:
@@ -75,16 +76,113 @@ def load() -> ctypes.CDLL:
             f"{LIB_PATH} not found: build it with `python -m adaprompt_b200.build` (needs nvcc, sm_100a). "
             "There is no CPU fallback.")
     lib = ctypes.CDLL(LIB_PATH)
+    ns = types.SimpleNamespace(_cdll=lib)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
-    return lib
+        setattr(ns, name, _traced(name, fn) if name in KERNELS_PER_CALL else fn)
+    _lib = ns
+    return ns
+
+
+# ---------------------------------------------------------------------------------------------------
+# launch accounting / per-launch timing (bench.py: gpu_launches, roofline; no effect on results)
+# ---------------------------------------------------------------------------------------------------
+KERNELS_PER_CALL = {
+    "af_gemm_bf16": 1, "af_conv3x3_bf16": 1, "af_attention_bf16": 1, "af_groupnorm_silu": 2, "af_layernorm": 1,
+    "af_conv_in": 1, "af_conv_out": 1, "af_timestep_embedding": 1, "af_linear_small": 1, "af_cast_bf16": 1,
+    "af_upsample2x_cast": 1, "af_cfg_ddim_update": 1, "af_advance_step": 1,
+}
+
+
+def _cost(name, a):
+    """(algorithmic flops, algorithmic bytes) of one call, from its C arguments."""
+    if name == "af_gemm_bf16":
+        K, M, N = a[2] + a[5], a[7], a[8]
+        return 2.0 * M * N * K, 2.0 * (M * K + N * K) + 2.0 * M * N
+    if name == "af_conv3x3_bf16":
+        C, B, H, W, Co, s = a[1] + a[3], a[5], a[6], a[7], a[8], a[9]
+        px = B * (H // s) * (W // s)
+        return 2.0 * px * Co * 9 * C, 2.0 * (B * H * W * C + 9 * C * Co) + 4.0 * px * Co
+    if name == "af_attention_bf16":
+        B, h, Nq, Nk, d = a[9], a[10], a[11], a[12], a[13]
+        return 4.0 * B * h * Nq * Nk * d, 2.0 * B * h * d * (2 * Nq + 2 * Nk)
+    if name == "af_groupnorm_silu":
+        n = a[4] * a[5] * (a[1] + a[3])
+        return 8.0 * n, 6.0 * n + (2.0 * n if a[11] else 0.0)
+    if name == "af_layernorm":
+        n = a[1] * a[2]
+        return 8.0 * n, 6.0 * n
+    return 0.0, 0.0
+
+
+class _Trace:
+    count = 0          # kernels launched through the C ABI since import
+    records = None     # list of (name, start_event, end_event, flops, bytes) while profiling
+
+
+TRACE = _Trace()
+
+
+def _traced(name, fn):
+    nk = KERNELS_PER_CALL[name]
+
+    def call(*args):
+        TRACE.count += nk
+        if TRACE.records is None:
+            return fn(*args)
+        import torch
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        fl, by = _cost(name, args)
+        TRACE.records.append((name, e0, e1, fl, by))
+        return rc
+
+    call.__name__ = name
+    return call
+
+
+class profile:
+    """with _lib.profile() as recs: ...  -> recs.summary() after a synchronize: per-entry-point launch count,
+    total device ms (CUDA events on the launching stream), algorithmic flops / bytes."""
+
+    def __enter__(self):
+        TRACE.records = []
+        self.records = TRACE.records
+        return self
+
+    def __exit__(self, *exc):
+        TRACE.records = None
+        return False
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, fl, by in self.records:
+            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += fl
+            d["bytes"] += by
+        return out
+
+
+SYNC_DEBUG = os.environ.get("AF_SYNC_DEBUG", "0") == "1"
 
 
 def check(rc: int, what: str) -> None:
     if rc == 0:
+        if SYNC_DEBUG:  # debugging aid: surface asynchronous kernel faults at the launch that caused them
+            import torch
+            try:
+                torch.cuda.synchronize()
+            except Exception as e:  # noqa: BLE001
+                raise AdaFaceB200Error(f"{what}: kernel fault detected right after launch: {e}") from e
         return
     msg = load().af_last_error().decode(errors="replace")
     if rc < 0:

@@ -196,8 +196,8 @@ class CrossAttention(PackedModule):
         vb = kb if v_ctx is k_ctx else padded_bf16(v_ctx.float())
         k = torch.empty(B * nk_pad, pk["wk"].shape[0], dtype=torch.bfloat16, device=dev)
         ops.gemm(kb, pk["wk"], k)
-        vt = torch.empty(pk["wv"].shape[0], B * nk_pad, dtype=torch.bfloat16, device=dev)
-        ops.gemm(pk["wv"], vb, vt, bn=128)
+        vt = torch.zeros(pk["wv"].shape[0], max(64, B * nk_pad), dtype=torch.bfloat16, device=dev)
+        ops.gemm(pk["wv"], vb, vt, bn=128, ldo=vt.shape[1])
         kv = ContextKV(k, vt, nk, nk_pad, B, ((k_ctx, k_ctx.data_ptr(), k_ctx._version),
                                                (v_ctx, v_ctx.data_ptr(), v_ctx._version)))
         self.__dict__["_kv_cache"] = kv
@@ -216,19 +216,21 @@ class CrossAttention(PackedModule):
         if kv is None:
             qk = torch.empty(T, 2 * h * dp, dtype=torch.bfloat16, device=dev)
             ops.gemm(x_ln, pk["wqk"], qk)
-            vt = torch.empty(C, T, dtype=torch.bfloat16, device=dev)
-            ops.gemm(pk["wv"], x_ln, vt, bn=256 if T % 256 == 0 else 128)
+            ldvt = max(64, (T + 7) // 8 * 8)  # V^T row pitch: TMA wants >= one 128-byte swizzle row
+            # pad columns must be finite (masked keys still enter P.V as 0 * v): zero-fill the rare padded case
+            vt = (torch.zeros if ldvt != T else torch.empty)(C, ldvt, dtype=torch.bfloat16, device=dev)
+            ops.gemm(pk["wv"], x_ln, vt, bn=256 if T % 256 == 0 else 128, ldo=ldvt)
             q, k, ldq, ldk = qk, qk[:, h * dp:], 2 * h * dp, 2 * h * dp
-            nk, vt_stride, ldvt = N, N, T
+            nk, kv_stride = N, N
         else:
             if kv.B != B:
                 raise ValueError(f"context batch {kv.B} != query batch {B}")
             q = torch.empty(T, h * dp, dtype=torch.bfloat16, device=dev)
             ops.gemm(x_ln, pk["wq"], q)
             k, vt, ldq, ldk = kv.k, kv.vt, h * dp, h * dp
-            nk, vt_stride, ldvt = kv.nk, kv.nk_pad, B * kv.nk_pad
+            nk, kv_stride, ldvt = kv.nk, kv.nk_pad, kv.vt.shape[1]
         o = torch.empty(T, C, dtype=torch.bfloat16, device=dev)
-        ops.attention(q, k, vt, o, B=B, heads=h, Nq=N, Nk=nk, d=d, ldq=ldq, ldk=ldk, ldvt=ldvt, vt_stride=vt_stride,
+        ops.attention(q, k, vt, o, B=B, heads=h, Nq=N, Nk=nk, d=d, ldq=ldq, ldk=ldk, ldvt=ldvt, kv_stride=kv_stride,
                       key_mask=key_mask)
         ops.gemm(o, pk["wo"], out, bias=pk["bo"], residual=residual)
         return out

@@ -349,12 +349,15 @@ static int launch_attention(const AttnParams& p, cudaStream_t stream) {
 using namespace af;
 
 extern "C" int af_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt,
-                                 long long ldvt, int vt_stride, const unsigned char* key_mask, void* O, int B,
+                                 long long ldvt, int kv_stride, const unsigned char* key_mask, void* O, int B,
                                  int heads, int Nq, int Nk, int d, cudaStream_t stream) {
   AF_CHECK_ARG(Q && K && Vt && O, "af_attention_bf16: null pointer");
   AF_CHECK_ARG(d == 40 || d == 80 || d == 160, "af_attention_bf16: head dim %d unsupported (40/80/160)", d);
-  AF_CHECK_ARG(B > 0 && heads > 0 && Nq > 0 && Nk > 0, "af_attention_bf16: bad sizes");
+  AF_CHECK_ARG(B > 0 && heads > 0 && Nq > 0 && Nk > 0 && kv_stride >= Nk, "af_attention_bf16: bad sizes");
   AF_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldvt % 8 == 0, "af_attention_bf16: leading dims must be multiples of 8");
+  AF_CHECK_ARG(ldvt >= 64, "af_attention_bf16: ldvt=%lld must be >= 64 (one 128-byte swizzle row)", ldvt);
+  // TMA needs every box to start on a 16-byte boundary: sample b's keys start at column b*kv_stride of V^T
+  AF_CHECK_ARG(B == 1 || kv_stride % 8 == 0, "af_attention_bf16: kv_stride=%d must be a multiple of 8 when B > 1", kv_stride);
   AttnParams p;
   memset(&p, 0, sizeof(p));
   const int dp = d == 40 ? 48 : d;
@@ -363,15 +366,17 @@ extern "C" int af_attention_bf16(const void* Q, long long ldq, const void* K, lo
   AF_CHECK_ARG(ldq >= static_cast<long long>(heads) * dp && ldk >= static_cast<long long>(heads) * dp,
                "af_attention_bf16: ldq/ldk smaller than heads*%d", dp);
   {
-    uint64_t dims[3] = {static_cast<uint64_t>(ldq), static_cast<uint64_t>(Nq), static_cast<uint64_t>(B)};
+    // dim 0 is the valid width (heads*dp), not the row pitch: boxes of the last head that stick out are
+    // zero-filled instead of reading whatever follows (e.g. the K half of a fused [Q|K] buffer)
+    uint64_t dims[3] = {static_cast<uint64_t>(heads) * dp, static_cast<uint64_t>(Nq), static_cast<uint64_t>(B)};
     uint64_t str[2] = {static_cast<uint64_t>(ldq) * 2, static_cast<uint64_t>(Nq) * ldq * 2};
     uint32_t box[3] = {64, 128, 1};
     int rc = make_tmap_bf16(&p.tmQ, Q, 3, dims, str, box);
     if (rc) return rc;
   }
   {
-    uint64_t dims[3] = {static_cast<uint64_t>(ldk), static_cast<uint64_t>(Nk), static_cast<uint64_t>(B)};
-    uint64_t str[2] = {static_cast<uint64_t>(ldk) * 2, static_cast<uint64_t>(Nk) * ldk * 2};
+    uint64_t dims[3] = {static_cast<uint64_t>(heads) * dp, static_cast<uint64_t>(Nk), static_cast<uint64_t>(B)};
+    uint64_t str[2] = {static_cast<uint64_t>(ldk) * 2, static_cast<uint64_t>(kv_stride) * ldk * 2};
     uint32_t box[3] = {64, static_cast<uint32_t>(bn), 1};
     int rc = make_tmap_bf16(&p.tmK, K, 3, dims, str, box);
     if (rc) return rc;
@@ -383,7 +388,7 @@ extern "C" int af_attention_bf16(const void* Q, long long ldq, const void* K, lo
     int rc = make_tmap_bf16(&p.tmV, Vt, 2, dims, str, box);
     if (rc) return rc;
   }
-  p.B = B; p.heads = heads; p.Nq = Nq; p.Nk = Nk; p.d = d; p.dp = dp; p.vt_stride = vt_stride;
+  p.B = B; p.heads = heads; p.Nq = Nq; p.Nk = Nk; p.d = d; p.dp = dp; p.vt_stride = kv_stride;
   p.key_mask = key_mask;
   p.out = static_cast<__nv_bfloat16*>(O);
   p.ldo = static_cast<long long>(heads) * d;

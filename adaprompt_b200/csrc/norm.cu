@@ -22,6 +22,9 @@ constexpr int kGroups = 32;
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x0, int C0,
                                                        const float* __restrict__ x1, int C1, int HW, int chunks,
                                                        float* __restrict__ partial /* [B, chunks, 32, 2] */) {
+  // Deterministic: every thread parks its per-channel partials in shared memory and one thread per group
+  // sums them in a fixed order (no floating-point atomics anywhere in the GroupNorm path).
+  extern __shared__ float s_part[];  // [slots][8]: 4 channel sums, 4 channel sums of squares
   const int C = C0 + C1;
   const int cq = C >> 2;             // channel quads per pixel
   const int cpg = C / kGroups;
@@ -30,70 +33,52 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
   const int pix_per_chunk = (HW + chunks - 1) / chunks;
   const int p_begin = chunk * pix_per_chunk;
   const int p_end = min(HW, p_begin + pix_per_chunk);
+  const bool narrow = cq <= 256;
+  const int ppb = narrow ? 256 / cq : 1;          // pixels handled per block iteration
+  const int slots = narrow ? ppb * cq : cq;
 
-  __shared__ float s_sum[kGroups], s_sq[kGroups];
-  if (threadIdx.x < kGroups) {
-    s_sum[threadIdx.x] = 0.f;
-    s_sq[threadIdx.x] = 0.f;
-  }
-  __syncthreads();
-
-  // threads are laid out so that a fixed thread always sees the same channel quad
-  const int tpp = cq;                               // threads needed per pixel
-  const int ppb = max(1, 256 / tpp);                // pixels per block-iteration (if cq <= 256)
-  if (tpp <= 256) {
-    const int my_q = threadIdx.x % tpp;
-    const int my_p = threadIdx.x / tpp;
-    if (my_p < ppb) {
-      float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-      const int c = my_q * 4;
-      const float* src;
-      int cs, off;
-      if (c < C0) { src = x0; cs = C0; off = c; } else { src = x1; cs = C1; off = c - C0; }
-      const float* base = src + static_cast<size_t>(b) * HW * cs + off;
-      for (int p = p_begin + my_p; p < p_end; p += ppb) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p) * cs));
-        s[0] += v.x; ss[0] += v.x * v.x;
-        s[1] += v.y; ss[1] += v.y * v.y;
-        s[2] += v.z; ss[2] += v.z * v.z;
-        s[3] += v.w; ss[3] += v.w * v.w;
-      }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int g = (c + e) / cpg;
-        atomicAdd(&s_sum[g], s[e]);
-        atomicAdd(&s_sq[g], ss[e]);
-      }
+  auto accumulate = [&](int q, int p_first, int p_step, int slot) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    const int c = q * 4;
+    const float* src;
+    int cs, off;
+    if (c < C0) { src = x0; cs = C0; off = c; } else { src = x1; cs = C1; off = c - C0; }
+    const float* base = src + static_cast<size_t>(b) * HW * cs + off;
+    for (int p = p_first; p < p_end; p += p_step) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p) * cs));
+      s[0] += v.x; ss[0] += v.x * v.x;
+      s[1] += v.y; ss[1] += v.y * v.y;
+      s[2] += v.z; ss[2] += v.z * v.z;
+      s[3] += v.w; ss[3] += v.w * v.w;
     }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      s_part[slot * 8 + e] = s[e];
+      s_part[slot * 8 + 4 + e] = ss[e];
+    }
+  };
+
+  if (narrow) {
+    // a fixed thread always sees the same channel quad; slot = pixel lane * cq + quad == threadIdx.x
+    if (threadIdx.x < slots) accumulate(threadIdx.x % cq, p_begin + threadIdx.x / cq, ppb, threadIdx.x);
   } else {
-    // wide rows (C > 1024): each thread walks several quads of every pixel
-    for (int q = threadIdx.x; q < cq; q += 256) {
-      float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-      const int c = q * 4;
-      const float* src;
-      int cs, off;
-      if (c < C0) { src = x0; cs = C0; off = c; } else { src = x1; cs = C1; off = c - C0; }
-      const float* base = src + static_cast<size_t>(b) * HW * cs + off;
-      for (int p = p_begin; p < p_end; ++p) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p) * cs));
-        s[0] += v.x; ss[0] += v.x * v.x;
-        s[1] += v.y; ss[1] += v.y * v.y;
-        s[2] += v.z; ss[2] += v.z * v.z;
-        s[3] += v.w; ss[3] += v.w * v.w;
-      }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int g = (c + e) / cpg;
-        atomicAdd(&s_sum[g], s[e]);
-        atomicAdd(&s_sq[g], ss[e]);
-      }
-    }
+    for (int q = threadIdx.x; q < cq; q += 256) accumulate(q, p_begin, 1, q);
   }
   __syncthreads();
   if (threadIdx.x < kGroups) {
-    float* o = partial + ((static_cast<size_t>(b) * chunks + chunk) * kGroups + threadIdx.x) * 2;
-    o[0] = s_sum[threadIdx.x];
-    o[1] = s_sq[threadIdx.x];
+    const int g = threadIdx.x;
+    float s = 0.f, ss = 0.f;
+    const int lanes = narrow ? ppb : 1;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      const int q = c >> 2, e = c & 3;
+      for (int l = 0; l < lanes; ++l) {
+        s += s_part[(l * cq + q) * 8 + e];
+        ss += s_part[(l * cq + q) * 8 + 4 + e];
+      }
+    }
+    float* o = partial + ((static_cast<size_t>(b) * chunks + chunk) * kGroups + g) * 2;
+    o[0] = s;
+    o[1] = ss;
   }
 }
 
@@ -235,13 +220,15 @@ extern "C" int af_groupnorm_silu(const float* x0, int C0, const float* x1, int C
   AF_CHECK_ARG(B > 0 && HW > 0 && C0 > 0 && C1 >= 0, "af_groupnorm_silu: bad sizes");
   AF_CHECK_ARG(C % 32 == 0 && C0 % 4 == 0 && C1 % 4 == 0, "af_groupnorm_silu: C0=%d C1=%d need C%%32==0, quads", C0, C1);
   AF_CHECK_ARG(C1 == 0 || x1 != nullptr, "af_groupnorm_silu: x1 null with C1=%d", C1);
-  AF_CHECK_ARG(C <= 8192, "af_groupnorm_silu: C=%d too large", C);
+  AF_CHECK_ARG(C <= 5120, "af_groupnorm_silu: C=%d too large", C);
   // enough chunks to fill the machine, few enough that pass 2 sums them cheaply
   int chunks = (2 * num_sms() + B - 1) / B;
   if (chunks > AF_GN_MAX_CHUNKS) chunks = AF_GN_MAX_CHUNKS;
   if (chunks > HW) chunks = HW;
   if (chunks < 1) chunks = 1;
-  gn_stats_kernel<<<dim3(chunks, B), 256, 0, stream>>>(x0, C0, x1, C1, HW, chunks, workspace);
+  const int cq = C / 4;
+  const size_t stats_smem = static_cast<size_t>(cq <= 256 ? (256 / cq) * cq : cq) * 8 * sizeof(float);
+  gn_stats_kernel<<<dim3(chunks, B), 256, stats_smem, stream>>>(x0, C0, x1, C1, HW, chunks, workspace);
   AF_LAUNCH_CHECK("gn_stats_kernel");
   const size_t total = static_cast<size_t>(HW) * (C / 4);
   int blocks = static_cast<int>((total + 256 * 8 - 1) / (256 * 8));

@@ -20,7 +20,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from .diffusion_util import make_ddim_sampling_parameters, make_ddim_timesteps, noise_like
 
 
@@ -33,6 +33,7 @@ class DDIMSampler(object):
         self.use_cuda_graph = kwargs.get("use_cuda_graph", True)
         self.verbose_progress = kwargs.get("progress", False)
         self._graphs = {}
+        self.graph_kernel_launches = 0   # kernels executed through CUDA-graph replays (bench.py: gpu_launches)
 
     def register_buffer(self, name, attr):
         if type(attr) == torch.Tensor:
@@ -238,6 +239,7 @@ class DDIMSampler(object):
         step_idx = torch.zeros(1, dtype=torch.int32, device=device)
         noise = torch.empty_like(x) if sigma_nonzero else None
         graphs = {}
+        kernels_in_graph = {}
 
         def build(cfg_on):
             nb = 2 * b if cfg_on else b
@@ -268,24 +270,28 @@ class DDIMSampler(object):
             step_idx.copy_(saved[1])
             t_buf.fill_(tvals[0])
             g = torch.cuda.CUDAGraph()
+            n0 = _lib.TRACE.count
             with torch.cuda.graph(g):
                 body()
+            kernels_in_graph[cfg_on] = _lib.TRACE.count - n0
             x.copy_(saved[0])
             step_idx.copy_(saved[1])
-            return g, t_buf
+            # the graph holds raw pointers: everything it reads or writes must stay referenced with it
+            return g, t_buf, (x_in, c2, coef_table, t_table, step_idx, x, pred, noise)
 
         for i in range(total):
             index = total - i - 1
             cfg_on = use_cfg[i]
             if cfg_on not in graphs:
                 graphs[cfg_on] = build(cfg_on)
-            g, t_buf = graphs[cfg_on]
+            g, t_buf, _keepalive = graphs[cfg_on]
             if i == 0 or use_cfg[i - 1] != cfg_on:
                 t_buf.fill_(tvals[i])
             unscaled = noise_like(x.shape, device, False)                   # keeps the RNG stream in step (:286)
             if noise is not None:
                 noise.copy_(unscaled)
             g.replay()
+            self.graph_kernel_launches += kernels_in_graph[cfg_on]
             if index % log_every_t == 0 or index == total - 1:
                 intermediates["x_inter"].append(x.clone())
                 intermediates["pred_x0"].append(pred.clone())

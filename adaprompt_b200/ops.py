@@ -109,7 +109,7 @@ def conv3x3(x0: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, *, x1: Option
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Tensor, *, B: int, heads: int, Nq: int,
-              Nk: int, d: int, ldq: int, ldk: int, ldvt: int, vt_stride: int,
+              Nk: int, d: int, ldq: int, ldk: int, ldvt: int, kv_stride: int,
               key_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
     for t, n in ((q, "q"), (k, "k"), (vt, "vt"), (out, "out")):
@@ -117,7 +117,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Ten
             raise ValueError(f"{n} must be a CUDA bf16 tensor")
     if key_mask is not None:
         _chk(key_mask, torch.uint8, "key_mask")
-    rc = lib.af_attention_bf16(q.data_ptr(), ldq, k.data_ptr(), ldk, vt.data_ptr(), ldvt, vt_stride, _p(key_mask),
+    rc = lib.af_attention_bf16(q.data_ptr(), ldq, k.data_ptr(), ldk, vt.data_ptr(), ldvt, kv_stride, _p(key_mask),
                                out.data_ptr(), B, heads, Nq, Nk, d, _stream())
     _lib.check(rc, "af_attention_bf16")
     return out

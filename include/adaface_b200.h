@@ -69,10 +69,11 @@ int af_conv3x3_bf16(const void* X0, int C0, const void* X1, int C1, const void* 
 
 /* Flash attention, 8-head SD-1.5 geometry (d in {40,80,160}); replaces attention.py:198-242.
  * Q [B,Nq,ldq], K [B,Nk,ldk] bf16 with head h at column h*DP (DP = 48 for d = 40, zero padded, else d);
- * Q pre-scaled by d^-1/2 * log2(e).  Vt [heads*d, ldvt] bf16 = V transposed, sample b at column b*vt_stride.
+ * Q pre-scaled by d^-1/2 * log2(e).  Vt [heads*d, ldvt] bf16 = V transposed.  Sample b's keys start at row
+ * b*kv_stride of K and at column b*kv_stride of Vt (kv_stride >= Nk; the cached 77-token context uses 80).
  * key_mask [B,Nk] bytes (1 = attend) or NULL (attention.py:223-232).  O [B,Nq,heads*d] bf16. */
 int af_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
-                      int vt_stride, const unsigned char* key_mask, void* O, int B, int heads, int Nq, int Nk, int d,
+                      int kv_stride, const unsigned char* key_mask, void* O, int B, int heads, int Nq, int Nk, int d,
                       af_stream_t stream);
 
 /* GroupNorm(32) over the channel concat [x0 | x1] of fp32 NHWC tensors, optional SiLU, bf16 output

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(lib):
     names = _declared()
     assert len(names) >= 17
     for n in names:
-        assert hasattr(lib, n), f"{n} declared in adaface_b200.h but not exported"
+        assert hasattr(lib._cdll, n), f"{n} declared in adaface_b200.h but not exported"
 
 
 def test_binding_table_matches_header():

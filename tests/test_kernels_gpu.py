@@ -158,10 +158,10 @@ def _attn_case(B, N, Nk, d, seed=0, mask=False, cross=False):
     qs = (q * (scale * math.log2(math.e))).to(torch.bfloat16)
     kb, vb = k.to(torch.bfloat16), v.to(torch.bfloat16)
     qbuf = torch.zeros(B, N, heads, dp, device=DEV, dtype=torch.bfloat16)
-    kbuf = torch.zeros(B, Nk, heads, dp, device=DEV, dtype=torch.bfloat16)
-    qbuf[..., :d] = qs
-    kbuf[..., :d] = kb
     nk_pad = ((Nk + 7) // 8) * 8 if cross else Nk
+    kbuf = torch.zeros(B, nk_pad, heads, dp, device=DEV, dtype=torch.bfloat16)
+    qbuf[..., :d] = qs
+    kbuf[:, :Nk, :, :d] = kb
     vt = torch.zeros(C, B * nk_pad, device=DEV, dtype=torch.bfloat16)
     vt.view(C, B, nk_pad)[:, :, :Nk] = vb.permute(2, 3, 0, 1).reshape(C, B, Nk)
     km = None
@@ -171,7 +171,7 @@ def _attn_case(B, N, Nk, d, seed=0, mask=False, cross=False):
         km[:, 0] = 1
     out = torch.empty(B, N, C, device=DEV, dtype=torch.bfloat16)
     ops.attention(qbuf, kbuf, vt, out, B=B, heads=heads, Nq=N, Nk=Nk, d=d, ldq=heads * dp, ldk=heads * dp,
-                  ldvt=B * nk_pad, vt_stride=nk_pad, key_mask=km)
+                  ldvt=B * nk_pad, kv_stride=nk_pad, key_mask=km)
     # reference: attention.py:198-242 on the same bf16-rounded operands (q carries scale*log2e -> use exp2)
     s = torch.einsum("bihd,bjhd->bhij", qs.float(), kb.float())
     if km is not None:
@@ -190,6 +190,66 @@ def test_self_attention(B, N, d):
 @pytest.mark.parametrize("B,N,d", [(2, 4096, 40), (2, 1024, 80), (2, 256, 160), (2, 64, 160)])
 def test_cross_attention_77(B, N, d):
     assert _attn_case(B, N, 77, d, seed=5, cross=True) < 6e-3
+
+
+@pytest.mark.parametrize("B,N,d", [(2, 1024, 40), (2, 256, 80), (3, 64, 160), (2, 16, 160)])
+def test_self_attention_fused_qk_buffer(B, N, d):
+    """Layout the UNet uses: one [tokens, Q|K] buffer (K = column view), V^T [C, tokens]."""
+    from adaprompt_b200 import ops
+    heads, C = 8, 8 * d
+    dp = 48 if d == 40 else d
+    q = _rand(B, N, heads, d, seed=11)
+    k = _rand(B, N, heads, d, seed=12)
+    v = _rand(B, N, heads, d, seed=13)
+    qs = (q * (d ** -0.5 * math.log2(math.e))).to(torch.bfloat16)
+    kb, vb = k.to(torch.bfloat16), v.to(torch.bfloat16)
+    qk = torch.zeros(B * N, 2, heads, dp, device=DEV, dtype=torch.bfloat16)
+    qk[:, 0, :, :d] = qs.reshape(B * N, heads, d)
+    qk[:, 1, :, :d] = kb.reshape(B * N, heads, d)
+    qk = qk.reshape(B * N, 2 * heads * dp)
+    ldvt = max(64, B * N)
+    vt = torch.zeros(C, ldvt, device=DEV, dtype=torch.bfloat16)
+    vt[:, :B * N] = vb.permute(2, 3, 0, 1).reshape(C, B * N)
+    out = torch.empty(B * N, C, device=DEV, dtype=torch.bfloat16)
+    ops.attention(qk, qk[:, heads * dp:], vt, out, B=B, heads=heads, Nq=N, Nk=N, d=d, ldq=2 * heads * dp,
+                  ldk=2 * heads * dp, ldvt=ldvt, kv_stride=N)
+    s = torch.einsum("bihd,bjhd->bhij", qs.float(), kb.float())
+    p = torch.softmax(s * math.log(2.0), dim=-1)
+    ref = torch.einsum("bhij,bjhd->bihd", p, vb.float()).reshape(B * N, C)
+    assert _rel(out, ref) < 6e-3
+
+
+def test_cross_attention_padded_kv_stride():
+    """Cached-context layout: 77 keys stored with a sample stride of 80 rows (K) / columns (V^T)."""
+    from adaprompt_b200 import ops
+    B, N, d, Nk, pad = 3, 256, 80, 77, 80
+    heads, C = 8, 640
+    q = _rand(B, N, heads, d, seed=21)
+    k = _rand(B, Nk, heads, d, seed=22)
+    v = _rand(B, Nk, heads, d, seed=23)
+    qs = (q * (d ** -0.5 * math.log2(math.e))).to(torch.bfloat16)
+    kb, vb = k.to(torch.bfloat16), v.to(torch.bfloat16)
+    kbuf = torch.zeros(B, pad, C, device=DEV, dtype=torch.bfloat16)
+    kbuf[:, :Nk] = kb.reshape(B, Nk, C)
+    vt = torch.zeros(C, B, pad, device=DEV, dtype=torch.bfloat16)
+    vt[:, :, :Nk] = vb.permute(2, 3, 0, 1).reshape(C, B, Nk)
+    out = torch.empty(B, N, C, device=DEV, dtype=torch.bfloat16)
+    ops.attention(qs.reshape(B * N, C).contiguous(), kbuf, vt, out, B=B, heads=heads, Nq=N, Nk=Nk, d=d, ldq=C, ldk=C,
+                  ldvt=B * pad, kv_stride=pad)
+    s = torch.einsum("bihd,bjhd->bhij", qs.float(), kb.float())
+    p = torch.softmax(s * math.log(2.0), dim=-1)
+    ref = torch.einsum("bhij,bjhd->bihd", p, vb.float()).reshape(B, N, C)
+    assert _rel(out, ref) < 6e-3
+
+
+def test_attention_rejects_unaligned_sample_stride():
+    """2x2 feature maps (N = 4) with B > 1 would put V^T boxes on 8-byte boundaries: refused, not mis-run."""
+    from adaprompt_b200 import ops
+    t = torch.zeros(8, 2560, device=DEV, dtype=torch.bfloat16)
+    vt = torch.zeros(1280, 64, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        ops.attention(t, t[:, 1280:], vt, torch.empty(8, 1280, device=DEV, dtype=torch.bfloat16), B=2, heads=8, Nq=4,
+                      Nk=4, d=160, ldq=2560, ldk=2560, ldvt=64, kv_stride=4)
 
 
 def test_self_attention_key_mask():

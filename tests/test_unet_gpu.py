@@ -62,11 +62,11 @@ def test_unet_eps_vs_reference_golden(unet, name):
 
 
 def test_unet_eps_vs_oracle_fresh_inputs(unet, state_dict):
-    """Oracle computed here on the box's CPU (16x16 latent keeps it to ~1 s)."""
+    """Oracle computed here on the box's CPU (32x32 latent keeps it to a few seconds)."""
     from oracle.golden_inputs import EXTRA_INFO
     from oracle.unet_oracle import UNetSpec, unet_forward
     g = torch.Generator().manual_seed(99)
-    x = torch.randn(2, 4, 16, 16, generator=g)
+    x = torch.randn(2, 4, 32, 32, generator=g)
     t = torch.tensor([741, 101])
     ctx = torch.randn(32, 77, 768, generator=g)
     with torch.no_grad():
