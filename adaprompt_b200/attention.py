@@ -171,11 +171,13 @@ class CrossAttention(PackedModule):
         self.__dict__["_kv_cache"] = None
 
     # ------------------------------------------------------------------ context K / V cache
-    def project_context(self, k_ctx: torch.Tensor, v_ctx: Optional[torch.Tensor] = None) -> ContextKV:
-        """K = to_k(k_ctx) [B, nk_pad, 8*dp], V^T = (to_v(v_ctx))^T [C, B*nk_pad] (attention.py:195-196)."""
+    def project_context(self, k_ctx: torch.Tensor, v_ctx: Optional[torch.Tensor] = None,
+                        out: Optional[ContextKV] = None) -> ContextKV:
+        """K = to_k(k_ctx) [B, nk_pad, 8*dp], V^T = (to_v(v_ctx))^T [C, B*nk_pad] (attention.py:195-196).
+        `out`: refresh an existing ContextKV in place (same buffers -> captured CUDA graphs stay valid)."""
         v_ctx = k_ctx if v_ctx is None else v_ctx
         c = self.__dict__.get("_kv_cache")
-        if c is not None:
+        if c is not None and out is None:
             (ks, kp, kver), (vs, vp, vver) = c.src
             if ks is k_ctx and vs is v_ctx and kp == k_ctx.data_ptr() and kver == k_ctx._version \
                     and vp == v_ctx.data_ptr() and vver == v_ctx._version:
@@ -194,12 +196,20 @@ class CrossAttention(PackedModule):
 
         kb = padded_bf16(k_ctx.float())
         vb = kb if v_ctx is k_ctx else padded_bf16(v_ctx.float())
-        k = torch.empty(B * nk_pad, pk["wk"].shape[0], dtype=torch.bfloat16, device=dev)
+        if out is not None:
+            if (out.B, out.nk, out.nk_pad) != (B, nk, nk_pad):
+                raise ValueError("project_context(out=...): shape changed")
+            k, vt = out.k, out.vt
+        else:
+            k = torch.empty(B * nk_pad, pk["wk"].shape[0], dtype=torch.bfloat16, device=dev)
+            vt = torch.zeros(pk["wv"].shape[0], max(64, B * nk_pad), dtype=torch.bfloat16, device=dev)
         ops.gemm(kb, pk["wk"], k)
-        vt = torch.zeros(pk["wv"].shape[0], max(64, B * nk_pad), dtype=torch.bfloat16, device=dev)
         ops.gemm(pk["wv"], vb, vt, bn=128, ldo=vt.shape[1])
-        kv = ContextKV(k, vt, nk, nk_pad, B, ((k_ctx, k_ctx.data_ptr(), k_ctx._version),
-                                               (v_ctx, v_ctx.data_ptr(), v_ctx._version)))
+        src = ((k_ctx, k_ctx.data_ptr(), k_ctx._version), (v_ctx, v_ctx.data_ptr(), v_ctx._version))
+        if out is not None:
+            out.src = src
+            return out
+        kv = ContextKV(k, vt, nk, nk_pad, B, src)
         self.__dict__["_kv_cache"] = kv
         return kv
 

@@ -81,6 +81,20 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+// 32 lanes x 32 columns into 32 consecutive registers of a larger per-thread array
+__device__ __forceinline__ void tmem_ld32p(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
 template <int D>
 __global__ void __launch_bounds__(192, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   using C = AttnCfg<D>;
@@ -225,21 +239,29 @@ __global__ void __launch_bounds__(192, 1) attention_kernel(const __grid_constant
       const int key0 = j * BN;
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(s_addr + c, v);
-        tmem_ld_wait();
+      // whole score row -> registers (one TMEM read), then everything below is branch-free straight-line code
+      float sc[BN];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int key = key0 + c + e;
+      for (int c = 0; c < BN; c += 32) tmem_ld32p(s_addr + c, reinterpret_cast<uint32_t*>(sc) + c);
+      tmem_ld_wait();
+      if (key0 + BN > p.Nk || mrow != nullptr) {  // warp-uniform: only the tail block / an explicit key mask
+#pragma unroll
+        for (int e = 0; e < BN; ++e) {
+          const int key = key0 + e;
           bool ok = key < p.Nk;
-          if (mrow && ok) ok = mrow[key] != 0;
-          if (ok) mx = fmaxf(mx, __uint_as_float(v[e]));
+          if (mrow != nullptr) ok = ok && (__ldg(mrow + min(key, p.Nk - 1)) != 0);
+          sc[e] = ok ? sc[e] : -INFINITY;
         }
       }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int e = 0; e < BN; e += 4) {
+        mx4[0] = fmaxf(mx4[0], sc[e]);
+        mx4[1] = fmaxf(mx4[1], sc[e + 1]);
+        mx4[2] = fmaxf(mx4[2], sc[e + 2]);
+        mx4[3] = fmaxf(mx4[3], sc[e + 3]);
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m_run, mx);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = fast_exp2(m_run - m_use);  // 0 on the first block
@@ -261,35 +283,26 @@ __global__ void __launch_bounds__(192, 1) attention_kernel(const __grid_constant
           tmem_st_wait();
         }
       }
-      l_run *= alpha;
-      // pass 2: P = exp2(S - m) -> bf16 -> swizzled smem
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(s_addr + c, v);
-        tmem_ld_wait();
-        float pv[32];
+      // P = exp2(S - m) -> bf16 -> swizzled smem; four independent partial sums keep the FADD chain short
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int key = key0 + c + e;
-          bool ok = key < p.Nk;
-          if (mrow && ok) ok = mrow[key] != 0;
-          const float x = ok ? fast_exp2(__uint_as_float(v[e]) - m_use) : 0.f;
-          pv[e] = x;
-          l_run += x;
-        }
-        uint8_t* atom = p_row + (c >> 6) * (128 * 128);
-        const int chunk0 = (c & 63) >> 3;  // 16-byte chunk index inside the 128-byte row
+      for (int c8 = 0; c8 < BN; c8 += 8) {
+        float pe[8];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 pk;
-          pk.x = pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]);
-          pk.y = pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]);
-          pk.z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]);
-          pk.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
-          *reinterpret_cast<uint4*>(atom + (((chunk0 + g) ^ sw) << 4)) = pk;
+        for (int e = 0; e < 8; ++e) {
+          pe[e] = fast_exp2(sc[c8 + e] - m_use);
+          l4[e & 3] += pe[e];
         }
+        uint4 pk;
+        pk.x = pack_bf16x2(pe[0], pe[1]);
+        pk.y = pack_bf16x2(pe[2], pe[3]);
+        pk.z = pack_bf16x2(pe[4], pe[5]);
+        pk.w = pack_bf16x2(pe[6], pe[7]);
+        uint8_t* atom = p_row + (c8 >> 6) * (128 * 128);
+        const uint32_t chunk = static_cast<uint32_t>((c8 & 63) >> 3);  // 16-byte chunk inside the 128-byte row
+        *reinterpret_cast<uint4*>(atom + ((chunk ^ sw) << 4)) = pk;
       }
+      l_run = l_run * alpha + ((l4[0] + l4[1]) + (l4[2] + l4[3]));
       m_run = m_new;
       fence_async_smem();
       tc_fence_before();

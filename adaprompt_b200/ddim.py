@@ -141,8 +141,9 @@ class DDIMSampler(object):
             for i in range(total_steps):
                 scales.append(g)
                 g = g - guide_scale_step_delta if i <= max_guide_anneal_steps else 1
-            return self._graph_sampling(img, cond, unconditional_conditioning, steps, scales, temperature,
-                                        log_every_t, intermediates)
+            from . import graph_sampler
+            return graph_sampler.run(self, img, cond, unconditional_conditioning, steps, scales, temperature,
+                                     log_every_t, intermediates)
 
         for i, step in enumerate(steps):
             index = total_steps - i - 1

@@ -71,6 +71,14 @@ class LatentDiffusionLite(nn.Module):
         b = self.sqrt_one_minus_alphas_cumprod[t].reshape(-1, *((1,) * (x_start.dim() - 1)))
         return a * x_start + b * noise
 
+    def refresh_conditioning(self, cond, batch: int):
+        """Hook for the CUDA-graph sampler: (re)project the conditioning tuple's context through the 16
+        cross-attention to_k / to_v layers now - in place when `cond[0]` is a static buffer whose content
+        changed.  Returns the {layer: ContextKV} dict so the caller can detect re-allocation."""
+        c_static_emb, _, extra_info = cond
+        iter_type = (extra_info or {}).get("iter_type", "normal_recon")
+        return self.model.diffusion_model.context_kv(c_static_emb, batch, iter_type)
+
     def apply_model(self, x_noisy, t, cond, return_ids=False):
         """ddpm.py:2192-2201,2292."""
         if not isinstance(cond, dict):

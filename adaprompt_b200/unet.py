@@ -413,13 +413,25 @@ class UNetModel(PackedModule):
     def context_kv(self, context: torch.Tensor, B: int, iter_type: str = "normal_recon"):
         """Projects the layerwise context [16*B, Nt, 768] (openaimodel.py:866) through to_k / to_v of the 16
         cross-attention layers ONCE; cached by tensor identity + version, so all DDIM steps and both CFG
-        branches reuse it.  Returns {layer_idx: ContextKV}."""
+        branches reuse it.  Returns {layer_idx: ContextKV}.  When the SAME tensor object is modified in place
+        (new prompt copied into a static buffer) the projections are refreshed into the same K / V^T buffers,
+        so CUDA graphs captured over them remain valid."""
         cache = self.__dict__.setdefault("_ctx_cache", [])
+        stale = None
         for ent in cache:
             src, ptr, ver, it, kvs = ent
-            if src is context and ptr == context.data_ptr() and ver == context._version and it == iter_type:
-                return kvs
+            if src is context and ptr == context.data_ptr() and it == iter_type:
+                if ver == context._version:
+                    return kvs
+                stale = ent
         ctx = context.reshape(B, 16, -1, context.shape[-1]).permute(1, 0, 2, 3)
+        if stale is not None:
+            for layer_idx, attn2 in self._ca_modules().items():
+                c = ctx[L2CA[layer_idx]].float().contiguous()
+                v_c, k_c = (t.contiguous() for t in c.chunk(2, dim=1)) if iter_type == "mix_hijk" else (c, c)
+                attn2.project_context(k_c, v_c, out=stale[4][layer_idx])
+            cache[cache.index(stale)] = (context, context.data_ptr(), context._version, iter_type, stale[4])
+            return stale[4]
         kvs = {}
         for layer_idx, attn2 in self._ca_modules().items():
             c = ctx[L2CA[layer_idx]].float().contiguous()
