@@ -117,6 +117,23 @@ def _cost(name, a):
     return 0.0, 0.0
 
 
+def _sig(name, a):
+    """Shape signature of one call (per-shape breakdown in bench.py --breakdown)."""
+    if name == "af_gemm_bf16":
+        ep = a[9]._obj
+        return f"M{a[7]} N{a[8]} K{a[2] + a[5]}{' geglu' if ep.geglu else ''}{' res' if ep.residual else ''}" \
+               f"{' f32' if ep.out_dtype == 0 else ''}"
+    if name == "af_conv3x3_bf16":
+        return f"B{a[5]} {a[6]}x{a[7]} C{a[1] + a[3]}->{a[8]} s{a[9]}"
+    if name == "af_attention_bf16":
+        return f"B{a[9]} Nq{a[11]} Nk{a[12]} d{a[13]}"
+    if name == "af_groupnorm_silu":
+        return f"B{a[4]} HW{a[5]} C{a[1] + a[3]}"
+    if name == "af_layernorm":
+        return f"rows{a[1]} C{a[2]}"
+    return ""
+
+
 class _Trace:
     count = 0          # kernels launched through the C ABI since import
     records = None     # list of (name, start_event, end_event, flops, bytes) while profiling
@@ -139,7 +156,7 @@ def _traced(name, fn):
         rc = fn(*args)
         e1.record()
         fl, by = _cost(name, args)
-        TRACE.records.append((name, e0, e1, fl, by))
+        TRACE.records.append((name, e0, e1, fl, by, _sig(name, args)))
         return rc
 
     call.__name__ = name
@@ -163,12 +180,15 @@ class profile:
         import torch
         torch.cuda.synchronize()
         out = {}
-        for name, e0, e1, fl, by in self.records:
-            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
-            d["launches"] += 1
-            d["ms"] += e0.elapsed_time(e1)
-            d["flops"] += fl
-            d["bytes"] += by
+        self.by_shape = {}
+        for name, e0, e1, fl, by, sig in self.records:
+            ms = e0.elapsed_time(e1)
+            for table, key in ((out, name), (self.by_shape, f"{name[3:]} {sig}")):
+                d = table.setdefault(key, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+                d["launches"] += 1
+                d["ms"] += ms
+                d["flops"] += fl
+                d["bytes"] += by
         return out
 
 

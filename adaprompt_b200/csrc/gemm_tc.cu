@@ -13,8 +13,9 @@
 //   * the skip-connection concat (openaimodel.py:1019) is never materialised: the K loop walks two
 //     tensor maps (A0 then A1).
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> fused bias / time-embedding / residual / GEGLU -> HBM).
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..9 = epilogue (TMEM -> registers -> smem transpose -> fused bias / time-embedding / residual /
+// GEGLU -> coalesced HBM stores).
 // smem ring of kStages {A 128x64, B BNx64} 128B-swizzled tiles; 2 TMEM accumulator stages so the
 // epilogue of tile i overlaps the mainloop of tile i+1.
 #include "../../include/adaface_b200.h"
@@ -48,24 +49,44 @@ struct GemmParams {
   int geglu;               // tile cols [0,BN/2) = value, [BN/2,BN) = gate; writes BN/2 cols
 };
 
+constexpr int kEpiWarps = 8;                    // 2 warps per TMEM lane quarter, each takes every other 32-col chunk
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;
+constexpr int kStagingBytes = kEpiWarps * 4096;  // 32 rows x 128 B per epilogue warp
+
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = BN <= 64 ? 8 : (BN <= 160 ? 6 : 4);
   static constexpr int kABytes = 128 * 128;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BN <= 64 ? 8 : (BN <= 128 ? 6 : (BN <= 160 ? 5 : 4));
   static constexpr int kAccStride = BN <= 128 ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccStride;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7): exact-GELU quality for a bf16 result at a third of the
+// instruction count of erff().
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = fast_exp2(-z * z * 1.4426950408889634f);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  const float erf_v = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_v);
+}
+
 template <int BN>
-__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* staging = smem + kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -85,7 +106,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], kEpiWarps);
     }
     mbar_fence_init();
   }
@@ -181,119 +202,128 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;
+    // TMEM is read row-per-thread (lane == row).  Each 32x32 fp32 chunk is transposed through a swizzled 4 KB
+    // shared-memory slab so that global traffic is coalesced: one warp instruction covers 4 rows x 128 B
+    // (fp32) instead of 32 rows x 16 B.
+    const int ew = warp - 2;
+    const int q = warp & 3;          // TMEM lane quarter this warp may access (hardware: warp id % 4)
+    const int half = ew >> 2;        // which 32-column chunks of the tile this warp takes
+    uint8_t* stg = staging + ew * 4096;
+    const int sub = lane >> 3;       // row within a group of 4 rows in the coalesced phase
+    const int cl = lane & 7;         // 16-byte column chunk within the 128-byte row
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
-      long long grow;
-      bool valid;
-      if (p.amode == 0) {
-        grow = static_cast<long long>(m_tile) * 128 + r;
-        valid = grow < p.M;
-      } else {
-        const int tw = m_tile % p.tiles_w;
-        const int th = (m_tile / p.tiles_w) % p.tiles_h;
-        const int tn = m_tile / (p.tiles_w * p.tiles_h);
-        const int rw = r % p.bw;
-        const int rh = (r / p.bw) % p.bh;
-        const int rn = r / (p.bw * p.bh);
-        const int n = tn * p.nb + rn, h = th * p.bh + rh, w = tw * p.bw + rw;
-        valid = n < p.B && h < p.H && w < p.W;
-        grow = (static_cast<long long>(n) * p.H + h) * p.W + w;
+      // rows this lane stores in the coalesced phase: tile row q*32 + 4k + sub, k = 0..7
+      long long grow[8];
+      uint32_t valid = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = q * 32 + 4 * k + sub;
+        if (p.amode == 0) {
+          grow[k] = static_cast<long long>(m_tile) * 128 + r;
+          if (grow[k] < p.M) valid |= 1u << k;
+        } else {
+          const int tw = m_tile % p.tiles_w;
+          const int th = (m_tile / p.tiles_w) % p.tiles_h;
+          const int tn = m_tile / (p.tiles_w * p.tiles_h);
+          const int rw = r % p.bw;
+          const int rh = (r / p.bw) % p.bh;
+          const int rn = r / (p.bw * p.bh);
+          const int n = tn * p.nb + rn, h = th * p.bh + rh, w = tw * p.bw + rw;
+          if (n < p.B && h < p.H && w < p.W) valid |= 1u << k;
+          grow[k] = (static_cast<long long>(n) * p.H + h) * p.W + w;
+        }
       }
-      const float* rb = nullptr;
-      if (p.rowbias && valid) rb = p.rowbias + (grow / p.rows_per_group) * p.ld_rowbias;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      constexpr int kOutCols = BN;   // accumulator columns per tile
+      const int out_cols = p.geglu ? kOutCols / 2 : kOutCols;
 
-      if (p.geglu) {
-        constexpr int HALF = BN / 2;
 #pragma unroll 1
-        for (int c = 0; c < HALF; c += 32) {
-          uint32_t v[32], g[32];
-          tmem_ld32(t_acc + c, v);
-          tmem_ld32(t_acc + HALF + c, g);
-          tmem_ld_wait();
-          const int pc = n_tile * BN + c;                  // packed column of the value half
-          const int oc = n_tile * HALF + c;                // output column
-          if (valid) {
+      for (int c = half * 32; c < out_cols; c += 64) {
+        const int col = (p.geglu ? n_tile * (BN / 2) : n_tile * BN) + c + 4 * cl;  // this lane's 4 output columns
+        const bool col_ok = col < (p.geglu ? p.N / 2 : p.N);
+        // 1. operands that do not depend on the accumulator are requested first: all eight residual rows are in
+        //    flight together (the output may alias the residual, so the loads must precede every store anyway)
+        float4 rs[8];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (pc + j >= p.N) break;
-              float o[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float xv = __uint_as_float(v[j + e]);
-                float xg = __uint_as_float(g[j + e]);
-                if (p.bias) {
-                  xv += __ldg(p.bias + pc + j + e);
-                  xg += __ldg(p.bias + pc + HALF + j + e);
-                }
-                o[e] = xv * gelu_erf_f(xg);
-              }
-              uint4 pk;
-              pk.x = pack_bf16x2(o[0], o[1]);
-              pk.y = pack_bf16x2(o[2], o[3]);
-              pk.z = pack_bf16x2(o[4], o[5]);
-              pk.w = pack_bf16x2(o[6], o[7]);
-              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + grow * p.ldo + oc + j) = pk;
+        for (int k = 0; k < 8; ++k) {
+          rs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (((valid >> k) & 1u) && col_ok) {
+            if (p.residual) rs[k] = *reinterpret_cast<const float4*>(p.residual + grow[k] * p.ldr + col);
+            if (p.rowbias) {
+              const float4 rb = __ldg(reinterpret_cast<const float4*>(
+                  p.rowbias + (grow[k] / p.rows_per_group) * p.ld_rowbias + col));
+              rs[k].x += rb.x; rs[k].y += rb.y; rs[k].z += rb.z; rs[k].w += rb.w;
             }
           }
         }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_acc + c, v);
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), bg4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && col_ok) {
+          if (p.geglu) {
+            const int pc = n_tile * BN + c + 4 * cl;  // packed column of the value half
+            b4 = __ldg(reinterpret_cast<const float4*>(p.bias + pc));
+            bg4 = __ldg(reinterpret_cast<const float4*>(p.bias + pc + BN / 2));
+          } else {
+            b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          }
+        }
+        // 2. accumulator chunk: TMEM (row per lane) -> swizzled slab -> registers (4 columns x 8 rows per lane)
+        uint32_t v[32];
+        tmem_ld32(t_acc + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        float4 a4[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int R = 4 * k + sub;
+          a4[k] = *reinterpret_cast<const float4*>(stg + R * 128 + ((cl ^ (R & 7)) << 4));
+          a4[k].x += b4.x; a4[k].y += b4.y; a4[k].z += b4.z; a4[k].w += b4.w;
+        }
+        if (p.geglu) {
+          __syncwarp();
+          tmem_ld32(t_acc + BN / 2 + c, v);
           tmem_ld_wait();
-          const int col0 = n_tile * BN + c;
-          if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const int col = col0 + j;
-              if (col >= p.N) break;
-              float o[8];
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
 #pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[j + e]);
-              if (p.bias) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
-                o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
-              }
-              if (rb) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb + col));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(rb + col + 4));
-                o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
-                o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
-              }
-              if (p.residual) {
-                const float* rp = p.residual + grow * p.ldr + col;
-                const float4 r0 = *reinterpret_cast<const float4*>(rp);
-                const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
-                o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w;
-                o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
-              }
-              if (p.out_bf16) {
-                uint4 pk;
-                pk.x = pack_bf16x2(o[0], o[1]);
-                pk.y = pack_bf16x2(o[2], o[3]);
-                pk.z = pack_bf16x2(o[4], o[5]);
-                pk.w = pack_bf16x2(o[6], o[7]);
-                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + grow * p.ldo + col) = pk;
-              } else {
-                float* op = static_cast<float*>(p.out) + grow * p.ldo + col;
-                *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<float4*>(op + 4) = make_float4(o[4], o[5], o[6], o[7]);
-              }
+          for (int k = 0; k < 8; ++k) {
+            const int R = 4 * k + sub;
+            const float4 g = *reinterpret_cast<const float4*>(stg + R * 128 + ((cl ^ (R & 7)) << 4));
+            a4[k].x *= gelu_fast(g.x + bg4.x);
+            a4[k].y *= gelu_fast(g.y + bg4.y);
+            a4[k].z *= gelu_fast(g.z + bg4.z);
+            a4[k].w *= gelu_fast(g.w + bg4.w);
+          }
+        }
+        // 3. coalesced stores: one warp instruction = 4 rows x 128 B (fp32) / 4 rows x 64 B (bf16)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (((valid >> k) & 1u) && col_ok) {
+            const float4 o = make_float4(a4[k].x + rs[k].x, a4[k].y + rs[k].y, a4[k].z + rs[k].z, a4[k].w + rs[k].w);
+            if (p.out_bf16) {
+              uint2 pk;
+              pk.x = pack_bf16x2(o.x, o.y);
+              pk.y = pack_bf16x2(o.z, o.w);
+              *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + grow[k] * p.ldo + col) = pk;
+            } else {
+              *reinterpret_cast<float4*>(static_cast<float*>(p.out) + grow[k] * p.ldo + col) = o;
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -326,7 +356,7 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BN><<<grid, 192, Cfg::kSmemBytes, stream>>>(p);
+  gemm_tc_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
   AF_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }

@@ -458,9 +458,11 @@ class UNetModel(PackedModule):
         e1 = torch.empty(B, pk["te0_w"].shape[0], dtype=torch.float32, device=dev)
         ops.linear_small(t_emb, pk["te0_w"], pk["te0_b"], e1, silu_out=True)              # :518-521
         emb = torch.empty(B, pk["te2_w"].shape[0], dtype=torch.float32, device=dev)
-        ops.linear_small(e1, pk["te2_w"], pk["te2_b"], emb)                               # :847
+        # emb is only ever consumed through the SiLU that opens every ResBlock.emb_layers (:222-228), so the
+        # activation is applied once here instead of once per output feature of the 22 projections
+        ops.linear_small(e1, pk["te2_w"], pk["te2_b"], emb, silu_out=True)                # :847 + SiLU of :223
         rows = torch.empty(B, pk["emb_total"], dtype=torch.float32, device=dev)
-        ops.linear_small(emb, pk["emb_w"], pk["emb_b"], rows, silu_in=True)               # :222-228 for all blocks
+        ops.linear_small(emb, pk["emb_w"], pk["emb_b"], rows)                             # :224-228 for all blocks
         return emb, rows
 
     def forward(self, x, timesteps=None, context=None, y=None, context_in=None, extra_info=None, **kwargs):

@@ -290,6 +290,10 @@ def main():
                 gb = v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0
                 print(f"{n:24s} launches {v['launches']:4d}  {v['ms']:8.3f} ms  {tf:8.1f} TFLOP/s  {gb:8.1f} GB/s",
                       file=sys.stderr)
+            for n, v in sorted(prof.by_shape.items(), key=lambda kv: -kv[1]["ms"])[:60]:
+                tf = v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0
+                gb = v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0
+                print(f"  {n:52s} x{v['launches']:3d} {v['ms']:8.3f} ms  {tf:7.1f} TF/s {gb:7.1f} GB/s", file=sys.stderr)
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample ---------------
     cpu_baseline = None
