@@ -44,13 +44,22 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     int cs, off;
     if (c < C0) { src = x0; cs = C0; off = c; } else { src = x1; cs = C1; off = c - C0; }
     const float* base = src + static_cast<size_t>(b) * HW * cs + off;
-    for (int p = p_first; p < p_end; p += p_step) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p) * cs));
+    auto acc = [&](const float4& v) {
       s[0] += v.x; ss[0] += v.x * v.x;
       s[1] += v.y; ss[1] += v.y * v.y;
       s[2] += v.z; ss[2] += v.z * v.z;
       s[3] += v.w; ss[3] += v.w * v.w;
+    };
+    int p = p_first;
+    // four independent 16-byte loads in flight per thread (memory-level parallelism), fixed summation order
+    for (; p + 3 * p_step < p_end; p += 4 * p_step) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p) * cs));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + p_step) * cs));
+      const float4 v2 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + 2 * p_step) * cs));
+      const float4 v3 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + 3 * p_step) * cs));
+      acc(v0); acc(v1); acc(v2); acc(v3);
     }
+    for (; p < p_end; p += p_step) acc(__ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p) * cs)));
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       s_part[slot * 8 + e] = s[e];
@@ -120,17 +129,23 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   __syncthreads();
 
   const int cq = C >> 2;
-  const size_t total = static_cast<size_t>(HW) * cq;
-  const size_t per_block = (total + gridDim.x - 1) / gridDim.x;
-  const size_t begin = blockIdx.x * per_block;
-  const size_t end = min(total, begin + per_block);
-  for (size_t i = begin + threadIdx.x; i < end; i += 256) {
-    const int p = static_cast<int>(i / cq);
-    const int c = static_cast<int>(i - static_cast<size_t>(p) * cq) * 4;
-    const float* src;
-    if (c < C0) src = x0 + (static_cast<size_t>(b) * HW + p) * C0 + c;
-    else src = x1 + (static_cast<size_t>(b) * HW + p) * C1 + (c - C0);
-    const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+  const uint32_t total = static_cast<uint32_t>(HW) * cq;   // quads per sample (< 2^31: 32-bit index math)
+  const uint32_t per_block = (total + gridDim.x - 1) / gridDim.x;
+  const uint32_t begin = blockIdx.x * per_block;
+  const uint32_t end = min(total, begin + per_block);
+  const float* xb0 = x0 + static_cast<size_t>(b) * HW * C0;
+  const float* xb1 = C1 ? x1 + static_cast<size_t>(b) * HW * C1 : nullptr;
+  auto src_of = [&](uint32_t i, int& c) -> const float* {
+    if (C1 == 0) {  // single source: the input is as dense as the output
+      c = static_cast<int>(i % static_cast<uint32_t>(cq)) * 4;
+      return xb0 + static_cast<size_t>(i) * 4;
+    }
+    const uint32_t p = i / static_cast<uint32_t>(cq);
+    c = static_cast<int>(i - p * cq) * 4;
+    if (c < C0) return xb0 + static_cast<size_t>(p) * C0 + c;
+    return xb1 + static_cast<size_t>(p) * C1 + (c - C0);
+  };
+  auto emit = [&](uint32_t i, int c, const float4& v) {
     float o0 = v.x * s_ab[c] + s_ab[C + c];
     float o1 = v.y * s_ab[c + 1] + s_ab[C + c + 1];
     float o2 = v.z * s_ab[c + 2] + s_ab[C + c + 2];
@@ -138,7 +153,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
     if (silu) {
       o0 = silu_f(o0); o1 = silu_f(o1); o2 = silu_f(o2); o3 = silu_f(o3);
     }
-    const size_t oidx = (static_cast<size_t>(b) * HW + p) * C + c;
+    const size_t oidx = static_cast<size_t>(b) * HW * C + static_cast<size_t>(i) * 4;  // dense concat: same quad index
     uint2 pk;
     pk.x = pack_bf16x2(o0, o1);
     pk.y = pack_bf16x2(o2, o3);
@@ -149,6 +164,20 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
       rk.y = pack_bf16x2(v.z, v.w);
       *reinterpret_cast<uint2*>(raw + oidx) = rk;
     }
+  };
+  uint32_t i = begin + threadIdx.x;
+  for (; i + 768 < end; i += 1024) {  // four independent 16-byte loads in flight per thread
+    int c0, c1, c2, c3;
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src_of(i, c0)));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src_of(i + 256, c1)));
+    const float4 v2 = __ldg(reinterpret_cast<const float4*>(src_of(i + 512, c2)));
+    const float4 v3 = __ldg(reinterpret_cast<const float4*>(src_of(i + 768, c3)));
+    emit(i, c0, v0); emit(i + 256, c1, v1); emit(i + 512, c2, v2); emit(i + 768, c3, v3);
+  }
+  for (; i < end; i += 256) {
+    int c;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src_of(i, c)));
+    emit(i, c, v);
   }
 }
 
@@ -222,7 +251,8 @@ extern "C" int af_groupnorm_silu(const float* x0, int C0, const float* x1, int C
   AF_CHECK_ARG(C1 == 0 || x1 != nullptr, "af_groupnorm_silu: x1 null with C1=%d", C1);
   AF_CHECK_ARG(C <= 5120, "af_groupnorm_silu: C=%d too large", C);
   // enough chunks to fill the machine, few enough that pass 2 sums them cheaply
-  int chunks = (2 * num_sms() + B - 1) / B;
+  int chunks = (8 * num_sms() + B - 1) / B;
+  if (chunks > HW / 16) chunks = HW / 16;   // keep >= 16 pixels per block
   if (chunks > AF_GN_MAX_CHUNKS) chunks = AF_GN_MAX_CHUNKS;
   if (chunks > HW) chunks = HW;
   if (chunks < 1) chunks = 1;
@@ -232,7 +262,7 @@ extern "C" int af_groupnorm_silu(const float* x0, int C0, const float* x1, int C
   AF_LAUNCH_CHECK("gn_stats_kernel");
   const size_t total = static_cast<size_t>(HW) * (C / 4);
   int blocks = static_cast<int>((total + 256 * 8 - 1) / (256 * 8));
-  const int cap = (8 * num_sms() + B - 1) / B;
+  const int cap = (16 * num_sms() + B - 1) / B;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   gn_apply_kernel<<<dim3(blocks, B), 256, 2 * C * sizeof(float), stream>>>(
