@@ -30,6 +30,7 @@ class AfEpilogue(Structure):
         ("ldo", c_longlong),
         ("out_dtype", c_int),
         ("geglu", c_int),
+        ("gn_stats", c_void_p),
     ]
 
 
@@ -44,12 +45,20 @@ SIGNATURES = {
                                 POINTER(AfEpilogue), c_int, c_void_p]),
     "af_attention_bf16": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_void_p,
                                   c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "af_groupnorm_workspace_bytes": (c_size_t, [c_int]),
+    "af_conv3x3_gn_slots": (c_int, [c_int, c_int]),
+    "af_groupnorm_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "af_groupnorm_stats_slots": (c_int, [c_int, c_int]),
+    "af_groupnorm_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "af_groupnorm_finalize": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                      c_void_p]),
+    "af_groupnorm_apply": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                   c_void_p, c_void_p, c_void_p]),
     "af_groupnorm_silu": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "af_layernorm": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
     "af_conv_in": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "af_conv_out": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "af_nhwc_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "af_timestep_embedding": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "af_linear_small": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "af_cast_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
@@ -57,6 +66,14 @@ SIGNATURES = {
     "af_cfg_ddim_update": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_longlong, c_void_p]),
     "af_advance_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "af_attention_small": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_longlong, c_int, c_int, c_int, c_int,
+                                   c_float, c_int, c_void_p]),
+    "af_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]),
+    "af_add_pos": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]),
+    "af_find_first_token": (c_int, [c_void_p, c_int, c_int, c_longlong, c_void_p, c_void_p]),
+    "af_splice_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "af_weighted_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_longlong,
+                                c_void_p]),
 }
 
 _lib = None
@@ -90,7 +107,10 @@ def load():
 # launch accounting / per-launch timing (bench.py: gpu_launches, roofline; no effect on results)
 # ---------------------------------------------------------------------------------------------------
 KERNELS_PER_CALL = {
-    "af_gemm_bf16": 1, "af_conv3x3_bf16": 1, "af_attention_bf16": 1, "af_groupnorm_silu": 2, "af_layernorm": 1,
+    "af_gemm_bf16": 1, "af_conv3x3_bf16": 1, "af_attention_bf16": 1, "af_groupnorm_silu": 3, "af_layernorm": 1,
+    "af_groupnorm_stats": 1, "af_groupnorm_finalize": 1, "af_groupnorm_apply": 1, "af_nhwc_to_nchw": 1,
+    "af_attention_small": 1, "af_gather_rows": 1, "af_add_pos": 1, "af_find_first_token": 1, "af_splice_rows": 1,
+    "af_weighted_sum": 1,
     "af_conv_in": 1, "af_conv_out": 1, "af_timestep_embedding": 1, "af_linear_small": 1, "af_cast_bf16": 1,
     "af_upsample2x_cast": 1, "af_cfg_ddim_update": 1, "af_advance_step": 1,
 }
@@ -100,17 +120,28 @@ def _cost(name, a):
     """(algorithmic flops, algorithmic bytes) of one call, from its C arguments."""
     if name == "af_gemm_bf16":
         K, M, N = a[2] + a[5], a[7], a[8]
-        return 2.0 * M * N * K, 2.0 * (M * K + N * K) + 2.0 * M * N
+        ep = a[9]._obj
+        No = N // 2 if ep.geglu else N
+        by = 2.0 * (M * K + N * K) + (4.0 if ep.out_dtype == 0 else 2.0) * M * No + (4.0 * M * No if ep.residual else 0.0)
+        return 2.0 * M * N * K, by
     if name == "af_conv3x3_bf16":
         C, B, H, W, Co, s = a[1] + a[3], a[5], a[6], a[7], a[8], a[9]
         px = B * (H // s) * (W // s)
-        return 2.0 * px * Co * 9 * C, 2.0 * (B * H * W * C + 9 * C * Co) + 4.0 * px * Co
+        ep = a[10]._obj
+        by = 2.0 * (B * H * W * C + 9 * C * Co) + (4.0 if ep.out_dtype == 0 else 2.0) * px * Co \
+            + (4.0 * px * Co if ep.residual else 0.0)
+        return 2.0 * px * Co * 9 * C, by
     if name == "af_attention_bf16":
         B, h, Nq, Nk, d = a[9], a[10], a[11], a[12], a[13]
         return 4.0 * B * h * Nq * Nk * d, 2.0 * B * h * d * (2 * Nq + 2 * Nk)
     if name == "af_groupnorm_silu":
         n = a[4] * a[5] * (a[1] + a[3])
         return 8.0 * n, 6.0 * n + (2.0 * n if a[11] else 0.0)
+    if name == "af_groupnorm_apply":
+        n = a[4] * a[5] * (a[1] + a[3])
+        return 8.0 * n, 6.0 * n + (2.0 * n if a[11] else 0.0)
+    if name == "af_groupnorm_stats":
+        return 0.0, 0.0  # overhead pass: its bytes are not algorithmic (the 6 B/element are charged to apply)
     if name == "af_layernorm":
         n = a[1] * a[2]
         return 8.0 * n, 6.0 * n
@@ -127,7 +158,7 @@ def _sig(name, a):
         return f"B{a[5]} {a[6]}x{a[7]} C{a[1] + a[3]}->{a[8]} s{a[9]}"
     if name == "af_attention_bf16":
         return f"B{a[9]} Nq{a[11]} Nk{a[12]} d{a[13]}"
-    if name == "af_groupnorm_silu":
+    if name in ("af_groupnorm_silu", "af_groupnorm_apply"):
         return f"B{a[4]} HW{a[5]} C{a[1] + a[3]}"
     if name == "af_layernorm":
         return f"rows{a[1]} C{a[2]}"

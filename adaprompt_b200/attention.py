@@ -360,7 +360,15 @@ class SpatialTransformer(PackedModule):
                 "b_out": self.proj_out.bias.detach().float().contiguous()}
 
     def _run(self, x: torch.Tensor, context, mask: Optional[torch.Tensor]) -> torch.Tensor:
-        """x fp32 NHWC [B,H,W,C] -> fp32 NHWC.  mask: float/bool [B,1,H0,W0] image mask or None."""
+        return self._run_act(x, context, mask).t
+
+    def _run_act(self, xa, context, mask: Optional[torch.Tensor]):
+        """xa: unet.Act or fp32 NHWC tensor [B,H,W,C] -> unet.Act (fp32 NHWC + the GroupNorm partial statistics the
+        proj_out epilogue wrote).  mask: float/bool [B,1,H0,W0] image mask or None."""
+        from .unet import Act
+        if not isinstance(xa, Act):
+            xa = Act(xa)
+        x = xa.t
         pk = self.packed()
         B, H, W, C = x.shape
         T = B * H * W
@@ -372,13 +380,14 @@ class SpatialTransformer(PackedModule):
             m2 = F.interpolate(mask.float(), size=(H, W), mode="nearest")
             km = m2.reshape(B, H * W).bool().to(torch.uint8).contiguous()
         xn = torch.empty(T, C, dtype=torch.bfloat16, device=dev)
-        ops.groupnorm_silu(x, pk["gn_w"], pk["gn_b"], pk["gn_eps"], False, xn)              # :325
+        ops.groupnorm_apply(x, xa.stats(), pk["gn_w"], pk["gn_b"], pk["gn_eps"], False, xn)  # :325
         t = torch.empty(T, pk["w_in"].shape[0], dtype=torch.float32, device=dev)
         ops.gemm(xn, pk["w_in"], t, bias=pk["b_in"])                                       # :326
         tb = block._run(t, B, H * W, block.resolve_context(context), km, out_dtype=torch.bfloat16)
         out = torch.empty(B, H, W, C, dtype=torch.float32, device=dev)
-        ops.gemm(tb, pk["w_out"], out, bias=pk["b_out"], residual=x)                        # :340-341
-        return out
+        st = ops.gn_stats_for_gemm(B, H * W, C, dev)
+        ops.gemm(tb, pk["w_out"], out, bias=pk["b_out"], residual=x, gn_stats=st.buf if st else None)  # :340-341
+        return Act(out, st)
 
     def forward(self, x, context=None, mask=None):
         """x NCHW [B,C,H,W] -> NCHW (reference layout)."""

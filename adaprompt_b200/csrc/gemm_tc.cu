@@ -47,6 +47,8 @@ struct GemmParams {
   long long ldo;
   int out_bf16;
   int geglu;               // tile cols [0,BN/2) = value, [BN/2,BN) = gate; writes BN/2 cols
+  float* gn_stats;         // [slots_total][N][2] per-channel (sum, sumsq) over 32-row quarters of the output, or null
+  int gn_slots;            // conv: stat slots per sample (= tiles_w * tiles_h * bw * bh / 32)
 };
 
 constexpr int kEpiWarps = 8;                    // 2 warps per TMEM lane quarter, each takes every other 32-col chunk
@@ -64,22 +66,20 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7): exact-GELU quality for a bf16 result at a third of the
-// instruction count of erff().
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float e = fast_exp2(-z * z * 1.4426950408889634f);
-  const float erf_abs = fmaf(-poly * t, e, 1.0f);
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
+// GELU for the GEGLU epilogue: x * Phi(x) in its tanh form, 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))), one MUFU
+// op per element.  |tanh form - erf form| <= 4.8e-4 absolute (rel-L2 2e-4 for unit-variance gates), an order of
+// magnitude below the bf16 rounding of the product this epilogue writes (rel-L2 1.7e-3); the erf form cost 3x the
+// instructions and left the tensor pipe idle 85 % of the time (profiles/r01_gemm_geglu_before.md).
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float x2 = x * x;
+  const float u = x * fmaf(0.0356774081f, x2, 0.7978845608f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
-template <int BN>
+template <int BN, bool GEGLU>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
@@ -202,135 +202,227 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    // TMEM is read row-per-thread (lane == row).  Each 32x32 fp32 chunk is transposed through a swizzled 4 KB
-    // shared-memory slab so that global traffic is coalesced: one warp instruction covers 4 rows x 128 B
-    // (fp32) instead of 32 rows x 16 B.
+    // TMEM is read row-per-thread (lane == row).  Global traffic is made coalesced by a transpose through a
+    // swizzled per-warp shared-memory slab.
     const int ew = warp - 2;
     const int q = warp & 3;          // TMEM lane quarter this warp may access (hardware: warp id % 4)
     const int half = ew >> 2;        // which 32-column chunks of the tile this warp takes
     uint8_t* stg = staging + ew * 4096;
-    const int sub = lane >> 3;       // row within a group of 4 rows in the coalesced phase
-    const int cl = lane & 7;         // 16-byte column chunk within the 128-byte row
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
-      // rows this lane stores in the coalesced phase: tile row q*32 + 4k + sub, k = 0..7
-      long long grow[8];
-      uint32_t valid = 0;
+
+    if constexpr (GEGLU) {
+      // ---- GEGLU (attention.py:32-39): out[:, j] = (acc[:, j] + bv[j]) * gelu(acc[:, BN/2 + j] + bg[j]), bf16.
+      // The math runs in the TMEM layout (one row per lane, 32 consecutive columns); only the bf16 result is
+      // transposed (2 KB per chunk) so that every warp store instruction writes 8 rows x 64 contiguous bytes.
+      const int orow = lane >> 2;      // row within a group of 8 rows in the coalesced phase
+      const int ochk = lane & 3;       // 16-byte chunk within the 64-byte bf16 row
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const long long row0 = static_cast<long long>(m_tile) * 128 + q * 32;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_acc = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+        for (int c = half * 32; c < BN / 2; c += 64) {
+          uint32_t v[32], g[32];
+          tmem_ld32(t_acc + c, v);
+          tmem_ld32(t_acc + BN / 2 + c, g);
+          const int pc = n_tile * BN + c;              // packed column of the value half (bias index)
+          const int col0 = n_tile * (BN / 2) + c;      // first output column of this chunk
+          const bool col_ok = col0 < p.N / 2;          // N/2 is a multiple of 128: chunks are all-or-nothing
+          tmem_ld_wait();
+          uint32_t pk[16];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int r = q * 32 + 4 * k + sub;
+          for (int j = 0; j < 8; ++j) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
+            if (p.bias && col_ok) {
+              bv = __ldg(reinterpret_cast<const float4*>(p.bias + pc) + j);
+              bg = __ldg(reinterpret_cast<const float4*>(p.bias + pc + BN / 2) + j);
+            }
+            const float o0 = (__uint_as_float(v[4 * j + 0]) + bv.x) * gelu_tanh(__uint_as_float(g[4 * j + 0]) + bg.x);
+            const float o1 = (__uint_as_float(v[4 * j + 1]) + bv.y) * gelu_tanh(__uint_as_float(g[4 * j + 1]) + bg.y);
+            const float o2 = (__uint_as_float(v[4 * j + 2]) + bv.z) * gelu_tanh(__uint_as_float(g[4 * j + 2]) + bg.z);
+            const float o3 = (__uint_as_float(v[4 * j + 3]) + bv.w) * gelu_tanh(__uint_as_float(g[4 * j + 3]) + bg.w);
+            pk[2 * j] = pack_bf16x2(o0, o1);
+            pk[2 * j + 1] = pack_bf16x2(o2, o3);
+          }
+          // slab: [32 rows][64 B], 16-byte chunks XOR-swizzled with (row >> 1) & 3 (conflict-free both ways)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int R = 8 * k + orow;
+            const uint4 o = *reinterpret_cast<const uint4*>(stg + R * 64 + ((ochk ^ ((R >> 1) & 3)) << 4));
+            const long long gr = row0 + R;
+            if (gr < p.M && col_ok)
+              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + gr * p.ldo + col0 + ochk * 8) = o;
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    } else {
+      // ---- generic: out = acc + bias[col] + rowbias[row / rows_per_group, col] + residual[row, col]  (fp32 | bf16)
+      // Each 32x32 fp32 chunk is transposed through a swizzled 4 KB slab: one warp instruction then covers
+      // 4 rows x 128 B (fp32).  The residual / rowbias operands of chunk c+1 are requested before chunk c is
+      // processed (and those of a tile's first chunk before its accumulator is complete), so the loads overlap
+      // the MMA wait, the TMEM read and the stores.
+      const int sub = lane >> 3;       // row within a group of 4 rows in the coalesced phase
+      const int cl = lane & 7;         // 16-byte column chunk within the 128-byte row
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        // rows this lane stores in the coalesced phase: tile row q*32 + 4k + sub, k = 0..7 (element offsets fit
+        // 32 bits: checked on the host)
+        uint32_t grow[8];              // output row index
+        uint32_t aoff[8];              // element offset of the row's auxiliary operand (residual, else rowbias)
+        uint32_t valid = 0;
+        long long stat_slot = -1;      // flat GroupNorm-statistics slot of this warp's 32 rows
         if (p.amode == 0) {
-          grow[k] = static_cast<long long>(m_tile) * 128 + r;
-          if (grow[k] < p.M) valid |= 1u << k;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            grow[k] = m_tile * 128 + q * 32 + 4 * k + sub;
+            if (grow[k] < static_cast<uint32_t>(p.M)) valid |= 1u << k;
+          }
+          stat_slot = static_cast<long long>(m_tile) * 4 + q;
         } else {
           const int tw = m_tile % p.tiles_w;
           const int th = (m_tile / p.tiles_w) % p.tiles_h;
           const int tn = m_tile / (p.tiles_w * p.tiles_h);
-          const int rw = r % p.bw;
-          const int rh = (r / p.bw) % p.bh;
-          const int rn = r / (p.bw * p.bh);
-          const int n = tn * p.nb + rn, h = th * p.bh + rh, w = tw * p.bw + rw;
-          if (n < p.B && h < p.H && w < p.W) valid |= 1u << k;
-          grow[k] = (static_cast<long long>(n) * p.H + h) * p.W + w;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int r = q * 32 + 4 * k + sub;
+            const int rw = r % p.bw;
+            const int rh = (r / p.bw) % p.bh;
+            const int rn = r / (p.bw * p.bh);
+            const int n = tn * p.nb + rn, h = th * p.bh + rh, w = tw * p.bw + rw;
+            if (n < p.B && h < p.H && w < p.W) valid |= 1u << k;
+            grow[k] = (n * p.H + h) * p.W + w;
+          }
+          const int per = p.bw * p.bh;                       // pixels of one sample inside the tile (>= 32 if stats)
+          const int n0s = tn * p.nb + (q * 32) / per;
+          if (n0s < p.B)
+            stat_slot = static_cast<long long>(n0s) * p.gn_slots + (th * p.tiles_w + tw) * (per >> 5) + (((q * 32) % per) >> 5);
         }
-      }
-
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_acc = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-      constexpr int kOutCols = BN;   // accumulator columns per tile
-      const int out_cols = p.geglu ? kOutCols / 2 : kOutCols;
-
-#pragma unroll 1
-      for (int c = half * 32; c < out_cols; c += 64) {
-        const int col = (p.geglu ? n_tile * (BN / 2) : n_tile * BN) + c + 4 * cl;  // this lane's 4 output columns
-        const bool col_ok = col < (p.geglu ? p.N / 2 : p.N);
-        // 1. operands that do not depend on the accumulator are requested first: all eight residual rows are in
-        //    flight together (the output may alias the residual, so the loads must precede every store anyway)
+        // ONE auxiliary fp32 operand is prefetched per row: the residual if present, else the per-sample rowbias.
+        // (Both together only occur in tests; the rowbias is then added at consumption time.)
+        const float* aux = p.residual ? p.residual : p.rowbias;
+        const bool late_rowbias = p.residual != nullptr && p.rowbias != nullptr;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (p.residual) aoff[k] = grow[k] * static_cast<uint32_t>(p.ldr);
+          else if (p.rowbias) aoff[k] = (grow[k] / static_cast<uint32_t>(p.rows_per_group)) * static_cast<uint32_t>(p.ld_rowbias);
+          else aoff[k] = 0;
+        }
+        const int ncols = p.N;
+        auto load_aux = [&](int c, float4 (&rs)[8]) {
+          const int col = n_tile * BN + c + 4 * cl;
+          const bool col_ok = col < ncols;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const bool ok = ((valid >> k) & 1u) && col_ok;
+            const float4* ptr = reinterpret_cast<const float4*>(aux + aoff[k] + (ok ? col : 0));
+            rs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) rs[k] = *ptr;
+          }
+        };
+        const bool has_aux = aux != nullptr;
         float4 rs[8];
+        if (has_aux) load_aux(half * 32, rs);
+        else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          rs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (((valid >> k) & 1u) && col_ok) {
-            if (p.residual) rs[k] = *reinterpret_cast<const float4*>(p.residual + grow[k] * p.ldr + col);
-            if (p.rowbias) {
-              const float4 rb = __ldg(reinterpret_cast<const float4*>(
-                  p.rowbias + (grow[k] / p.rows_per_group) * p.ld_rowbias + col));
-              rs[k].x += rb.x; rs[k].y += rb.y; rs[k].z += rb.z; rs[k].w += rb.w;
-            }
-          }
+          for (int k = 0; k < 8; ++k) rs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), bg4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && col_ok) {
-          if (p.geglu) {
-            const int pc = n_tile * BN + c + 4 * cl;  // packed column of the value half
-            b4 = __ldg(reinterpret_cast<const float4*>(p.bias + pc));
-            bg4 = __ldg(reinterpret_cast<const float4*>(p.bias + pc + BN / 2));
-          } else {
-            b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-          }
-        }
-        // 2. accumulator chunk: TMEM (row per lane) -> swizzled slab -> registers (4 columns x 8 rows per lane)
-        uint32_t v[32];
-        tmem_ld32(t_acc + c, v);
-        tmem_ld_wait();
+
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_acc = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+
+        constexpr int kChunkIters = (BN + 63) / 64;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-              make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        __syncwarp();
-        float4 a4[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int R = 4 * k + sub;
-          a4[k] = *reinterpret_cast<const float4*>(stg + R * 128 + ((cl ^ (R & 7)) << 4));
-          a4[k].x += b4.x; a4[k].y += b4.y; a4[k].z += b4.z; a4[k].w += b4.w;
-        }
-        if (p.geglu) {
-          __syncwarp();
-          tmem_ld32(t_acc + BN / 2 + c, v);
+        for (int it = 0; it < kChunkIters; ++it) {
+          const int c = half * 32 + it * 64;
+          if (c >= BN) break;
+          const int col = n_tile * BN + c + 4 * cl;  // this lane's 4 output columns
+          const bool col_ok = col < ncols;
+          uint32_t v[32];
+          tmem_ld32(t_acc + c, v);
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          float4 rsn[8];
+          const bool more = c + 64 < BN;
+          if (has_aux && more) load_aux(c + 64, rsn);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
                 make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           __syncwarp();
+          float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), q4 = s4;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const int R = 4 * k + sub;
-            const float4 g = *reinterpret_cast<const float4*>(stg + R * 128 + ((cl ^ (R & 7)) << 4));
-            a4[k].x *= gelu_fast(g.x + bg4.x);
-            a4[k].y *= gelu_fast(g.y + bg4.y);
-            a4[k].z *= gelu_fast(g.z + bg4.z);
-            a4[k].w *= gelu_fast(g.w + bg4.w);
-          }
-        }
-        // 3. coalesced stores: one warp instruction = 4 rows x 128 B (fp32) / 4 rows x 64 B (bf16)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (((valid >> k) & 1u) && col_ok) {
-            const float4 o = make_float4(a4[k].x + rs[k].x, a4[k].y + rs[k].y, a4[k].z + rs[k].z, a4[k].w + rs[k].w);
-            if (p.out_bf16) {
-              uint2 pk;
-              pk.x = pack_bf16x2(o.x, o.y);
-              pk.y = pack_bf16x2(o.z, o.w);
-              *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + grow[k] * p.ldo + col) = pk;
-            } else {
-              *reinterpret_cast<float4*>(static_cast<float*>(p.out) + grow[k] * p.ldo + col) = o;
+            const float4 a = *reinterpret_cast<const float4*>(stg + R * 128 + ((cl ^ (R & 7)) << 4));
+            float4 o = make_float4(a.x + b4.x + rs[k].x, a.y + b4.y + rs[k].y, a.z + b4.z + rs[k].z,
+                                   a.w + b4.w + rs[k].w);
+            if (((valid >> k) & 1u) && col_ok) {
+              if (late_rowbias) {
+                const float4 rb = __ldg(reinterpret_cast<const float4*>(
+                    p.rowbias + static_cast<long long>(grow[k] / static_cast<uint32_t>(p.rows_per_group)) * p.ld_rowbias + col));
+                o.x += rb.x; o.y += rb.y; o.z += rb.z; o.w += rb.w;
+              }
+              if (p.out_bf16) {
+                uint2 pk;
+                pk.x = pack_bf16x2(o.x, o.y);
+                pk.y = pack_bf16x2(o.z, o.w);
+                *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + grow[k] * static_cast<uint32_t>(p.ldo) + col) = pk;
+              } else {
+                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + grow[k] * static_cast<uint32_t>(p.ldo) + col) = o;
+              }
+              s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
+              q4.x = fmaf(o.x, o.x, q4.x); q4.y = fmaf(o.y, o.y, q4.y);
+              q4.z = fmaf(o.z, o.z, q4.z); q4.w = fmaf(o.w, o.w, q4.w);
             }
           }
+          if (p.gn_stats) {
+            // fixed-order reduction over the 4 row sub-groups (deterministic), lanes 0..7 publish 4 channels each
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              s4.x += __shfl_xor_sync(0xffffffffu, s4.x, o); s4.y += __shfl_xor_sync(0xffffffffu, s4.y, o);
+              s4.z += __shfl_xor_sync(0xffffffffu, s4.z, o); s4.w += __shfl_xor_sync(0xffffffffu, s4.w, o);
+              q4.x += __shfl_xor_sync(0xffffffffu, q4.x, o); q4.y += __shfl_xor_sync(0xffffffffu, q4.y, o);
+              q4.z += __shfl_xor_sync(0xffffffffu, q4.z, o); q4.w += __shfl_xor_sync(0xffffffffu, q4.w, o);
+            }
+            if (sub == 0 && col_ok && stat_slot >= 0) {
+              float4* dst = reinterpret_cast<float4*>(p.gn_stats + (stat_slot * ncols + col) * 2);
+              dst[0] = make_float4(s4.x, q4.x, s4.y, q4.y);
+              dst[1] = make_float4(s4.z, q4.z, s4.w, q4.w);
+            }
+          }
+          if (has_aux && more) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rs[k] = rsn[k];   // fully unrolled chunk loop: pure register renaming
+          }
+          __syncwarp();
         }
+        tc_fence_before();
         __syncwarp();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
       }
     }
   }
@@ -346,27 +438,28 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool GEGLU>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    AF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    AF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
+  gemm_tc_kernel<BN, GEGLU><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
   AF_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
 
 static int dispatch_gemm(int bn, const GemmParams& p, cudaStream_t stream) {
+  if (p.geglu) return launch_gemm<256, true>(p, stream);
   switch (bn) {
-    case 64: return launch_gemm<64>(p, stream);
-    case 128: return launch_gemm<128>(p, stream);
-    case 160: return launch_gemm<160>(p, stream);
-    case 256: return launch_gemm<256>(p, stream);
+    case 64: return launch_gemm<64, false>(p, stream);
+    case 128: return launch_gemm<128, false>(p, stream);
+    case 160: return launch_gemm<160, false>(p, stream);
+    case 256: return launch_gemm<256, false>(p, stream);
     default: set_error("unsupported BN %d (64/128/160/256)", bn); return -1;
   }
 }
@@ -393,12 +486,21 @@ static int fill_epilogue(GemmParams& p, const af_epilogue* ep, long long default
   p.ldo = ep->ldo > 0 ? ep->ldo : default_ldo;
   p.out_bf16 = ep->out_dtype == AF_DTYPE_BF16;
   p.geglu = ep->geglu;
+  p.gn_stats = ep->gn_stats;
+  AF_CHECK_ARG(!ep->gn_stats || (!ep->geglu && (reinterpret_cast<uintptr_t>(ep->gn_stats) & 15) == 0),
+               "epilogue: gn_stats needs the generic epilogue and a 16-byte aligned buffer");
   AF_CHECK_ARG(ep->out != nullptr, "epilogue: out is null");
   AF_CHECK_ARG(ep->out_dtype == AF_DTYPE_BF16 || ep->out_dtype == AF_DTYPE_F32, "epilogue: bad out dtype %d",
                ep->out_dtype);
   AF_CHECK_ARG(!ep->geglu || ep->out_dtype == AF_DTYPE_BF16, "geglu epilogue writes bf16 only");
   AF_CHECK_ARG(!ep->geglu || (!ep->residual && !ep->rowbias), "geglu epilogue: residual / rowbias unsupported");
   AF_CHECK_ARG((reinterpret_cast<uintptr_t>(ep->out) & 15) == 0, "epilogue: out not 16B aligned");
+  {
+    const long long lim = 1ll << 31, rows = p.M;
+    const long long groups = ep->rows_per_group > 0 ? rows / p.rows_per_group + 1 : 4096;  // conv: one group per image
+    AF_CHECK_ARG(rows * p.ldo < lim && rows * p.ldr < lim && (!p.rowbias || groups * p.ld_rowbias < lim),
+                 "epilogue: output / residual / rowbias larger than 2^31 elements");
+  }
   AF_CHECK_ARG(p.ldo % 8 == 0 && p.ldr % 4 == 0 && p.ld_rowbias % 4 == 0, "epilogue: ldo %lld / ldr %lld / ld_rowbias %lld misaligned", p.ldo, p.ldr, p.ld_rowbias);
   return 0;
 }
@@ -456,6 +558,23 @@ extern "C" int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* 
   return dispatch_gemm(bn, p, stream);
 }
 
+// output-pixel box of one 128-row conv tile: bw = largest power of two <= min(64, next_pow2(Wo)); rows / images
+// fill up to 128 pixels
+static void conv_tile_box(int Ho, int Wo, int* bw_, int* bh_, int* nb_) {
+  int bw = 1;
+  while (bw < Wo && bw < 64) bw <<= 1;
+  int bh = 1;
+  while (bh < Ho && bw * bh < 128) bh <<= 1;
+  *bw_ = bw; *bh_ = bh; *nb_ = 128 / (bw * bh);
+}
+
+extern "C" int af_conv3x3_gn_slots(int Ho, int Wo) {
+  int bw, bh, nb;
+  conv_tile_box(Ho, Wo, &bw, &bh, &nb);
+  if (bw * bh < 32) return 0;  // a 32-row quarter would straddle samples: use af_groupnorm_stats instead
+  return ((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * (bw * bh / 32);
+}
+
 extern "C" int af_conv3x3_bf16(const void* X0, int C0, const void* X1, int C1, const void* Wt, int B, int H, int W,
                                int Cout, int stride, const af_epilogue* ep, int bn_hint, cudaStream_t stream) {
   AF_CHECK_ARG(X0 && Wt && ep, "af_conv3x3_bf16: null pointer");
@@ -470,12 +589,8 @@ extern "C" int af_conv3x3_bf16(const void* X0, int C0, const void* X1, int C1, c
   const int Cin = C0 + C1;
   const int Ho = stride == 1 ? H : H / 2, Wo = stride == 1 ? W : W / 2;
   const int bn = pick_bn(Cout, 0, bn_hint);
-  // tile box: bw = largest power of two <= min(64, next_pow2(Wo)); rows/images fill up to 128 pixels
-  int bw = 1;
-  while (bw < Wo && bw < 64) bw <<= 1;
-  int bh = 1;
-  while (bh < Ho && bw * bh < 128) bh <<= 1;
-  int nb = 128 / (bw * bh);
+  int bw, bh, nb;
+  conv_tile_box(Ho, Wo, &bw, &bh, &nb);
   p.bw = bw; p.bh = bh; p.nb = nb;
   p.tiles_w = (Wo + bw - 1) / bw;
   p.tiles_h = (Ho + bh - 1) / bh;
@@ -527,5 +642,9 @@ extern "C" int af_conv3x3_bf16(const void* X0, int C0, const void* X1, int C1, c
   int rc = fill_epilogue(p, ep, Cout);
   if (rc) return rc;
   if (p.rowbias && ep->rows_per_group <= 0) p.rows_per_group = Ho * Wo;
+  if (p.gn_stats) {
+    p.gn_slots = af_conv3x3_gn_slots(Ho, Wo);
+    AF_CHECK_ARG(p.gn_slots > 0, "af_conv3x3_bf16: gn_stats unsupported for %dx%d outputs (fewer than 32 pixels per tile row group)", Ho, Wo);
+  }
   return dispatch_gemm(bn, p, stream);
 }

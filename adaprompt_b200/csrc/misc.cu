@@ -6,19 +6,27 @@
 namespace af {
 
 // ---------------------------------------------------------------------------------------------
-// conv_in: NCHW fp32 [B,Cin,H,W] (Cin small) -> NHWC fp32 [B,H,W,Cout], 3x3 pad 1, fp32 math.
+// conv_in: NCHW fp32 [B,Cin,H,W] (Cin = 4) -> NHWC fp32 [B,H,W,Cout], 3x3 pad 1, fp32 math.
 // Reference: UNetModel.input_blocks[0] = conv_nd(2, 4, 320, 3, padding=1) (openaimodel.py:527-533).
-// block = one row segment of 16 pixels; thread <-> output channel.
+// Block = 32 consecutive pixels of one image row; the weights live in shared memory as [tap*Cin + ci][Cout] so a
+// thread reads the four output channels it owns with one 16-byte load per tap, and the input value of a (pixel,
+// tap) is one broadcast load shared by all channel quads.  Stores are 512 B contiguous per warp (NHWC).
 // ---------------------------------------------------------------------------------------------
 template <int CIN>
-__global__ void __launch_bounds__(320) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(320, 2) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, float* __restrict__ y, int B,
                                                       int H, int W, int Cout) {
-  constexpr int TP = 16;
-  __shared__ float patch[CIN][3][TP + 2];
+  constexpr int TP = 32, TAPS = CIN * 9;
+  extern __shared__ float smem_ci[];
+  float* sw = smem_ci;                          // [TAPS][Cout]
+  float* patch = smem_ci + TAPS * Cout;         // [CIN][3][TP + 2]
   const int wt = blockIdx.x * TP;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
+  for (int i = threadIdx.x; i < TAPS * Cout; i += blockDim.x) {
+    const int co = i / TAPS, t = i - co * TAPS;          // global layout [co][ci][ky][kx]
+    sw[t * Cout + co] = w[i];
+  }
   for (int i = threadIdx.x; i < CIN * 3 * (TP + 2); i += blockDim.x) {
     const int c = i / (3 * (TP + 2));
     const int rr = (i / (TP + 2)) % 3;
@@ -26,24 +34,57 @@ __global__ void __launch_bounds__(320) conv_in_kernel(const float* __restrict__ 
     const int hh = h + rr - 1, ww = wt + cc - 1;
     float v = 0.f;
     if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((static_cast<size_t>(b) * CIN + c) * H + hh) * W + ww];
-    patch[c][rr][cc] = v;
+    patch[i] = v;
   }
   __syncthreads();
-  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
-    float wr[CIN * 9];
+  const int cq = Cout >> 2;                      // channel quads
+  const int groups = blockDim.x / cq;            // pixel groups served concurrently
+  const int pg = threadIdx.x / cq, q = threadIdx.x - pg * cq;
+  if (pg >= groups) return;
+  const int ppg = TP / groups;                   // pixels per group (host guarantees divisibility)
+  const float4 bv = bias ? *reinterpret_cast<const float4*>(bias + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p0 = 0; p0 < ppg; p0 += 8) {
+    float4 acc[8];
 #pragma unroll
-    for (int i = 0; i < CIN * 9; ++i) wr[i] = w[co * CIN * 9 + i];  // [co][ci][ky][kx]
-    const float bv = bias ? bias[co] : 0.f;
-    for (int px = 0; px < TP && wt + px < W; ++px) {
-      float acc = bv;
+    for (int i = 0; i < 8; ++i) acc[i] = bv;
+#pragma unroll 1
+    for (int c = 0; c < CIN; ++c)
 #pragma unroll
-      for (int c = 0; c < CIN; ++c)
+      for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4 wv = *reinterpret_cast<const float4*>(sw + ((c * 3 + ky) * 3 + kx) * Cout + q * 4);
+          const float* pr = patch + (c * 3 + ky) * (TP + 2) + pg * ppg + p0 + kx;
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) acc += wr[(c * 3 + ky) * 3 + kx] * patch[c][ky][px + kx];
-      y[((static_cast<size_t>(b) * H + h) * W + wt + px) * Cout + co] = acc;
+          for (int i = 0; i < 8; ++i) {
+            const float xv = pr[i];
+            acc[i].x = fmaf(wv.x, xv, acc[i].x); acc[i].y = fmaf(wv.y, xv, acc[i].y);
+            acc[i].z = fmaf(wv.z, xv, acc[i].z); acc[i].w = fmaf(wv.w, xv, acc[i].w);
+          }
+        }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int px = wt + pg * ppg + p0 + i;
+      if (px < W)
+        *reinterpret_cast<float4*>(y + ((static_cast<size_t>(b) * H + h) * W + px) * Cout + q * 4) = acc[i];
     }
+  }
+}
+
+// NHWC fp32 [B, HW, CP] -> NCHW fp32 [B, COUT, HW] (first COUT of the CP padded channels): the UNet's last
+// convolution runs on the tensor cores with Cout padded 4 -> 8; this restores the public layout.
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
+                                                           int HW, int CP, int COUT) {
+  const size_t total = static_cast<size_t>(B) * HW;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = i / HW, p = i - b * HW;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + i * CP));
+    float* o = y + b * COUT * HW + p;
+    o[0] = v.x;
+    if (COUT > 1) o[HW] = v.y;
+    if (COUT > 2) o[2 * static_cast<size_t>(HW)] = v.z;
+    if (COUT > 3) o[3 * static_cast<size_t>(HW)] = v.w;
   }
 }
 
@@ -121,43 +162,74 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __
 }
 
 // ---------------------------------------------------------------------------------------------
-// small-M fp32 linear: y[M,N] = act_out(act_in(x)[M,K] @ W[N,K]^T + b).  One warp per output feature.
+// small-M fp32 linear: y[M,N] = act_out(act_in(x)[M,K] @ W[N,K]^T + b).
 // Used for time_embed (openaimodel.py:518-522,847) and the 22 ResBlock emb_layers (:222-228,268), whose
-// weights are concatenated into one [sum Cout, 1280] matrix at load time.
+// weights are concatenated into one [sum Cout, 1280] matrix at load time.  Weight-read bound (113 MB fp32 per
+// UNet step): x (<= 16 rows per pass) is staged in shared memory with the input activation applied once, a warp
+// produces FOUR output features per pass so every shared-memory read of x is reused four times, and the weights
+// stream through 16-byte coalesced loads.
 // ---------------------------------------------------------------------------------------------
+constexpr int kLsRows = 16, kLsFeat = 4;
 __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ y,
                                                            int M, int N, int K, int silu_in, int silu_out) {
+  extern __shared__ float sx[];  // [kLsRows][K]
   const int lane = threadIdx.x & 31;
-  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (n >= N) return;
-  const float4* wr = reinterpret_cast<const float4*>(w + static_cast<size_t>(n) * K);
+  const int n0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kLsFeat;
   const int nvec = K >> 2;
-  for (int m0 = 0; m0 < M; m0 += 8) {
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int k = lane; k < nvec; k += 32) {
-      const float4 wv = __ldg(wr + k);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (m0 + i < M) {
-          float4 xv = __ldg(reinterpret_cast<const float4*>(x + static_cast<size_t>(m0 + i) * K) + k);
-          if (silu_in) {
-            xv.x = silu_f(xv.x); xv.y = silu_f(xv.y); xv.z = silu_f(xv.z); xv.w = silu_f(xv.w);
-          }
-          acc[i] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+  for (int m0 = 0; m0 < M; m0 += kLsRows) {
+    const int mr = min(kLsRows, M - m0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kLsRows * nvec; i += blockDim.x) {
+      const int r = i / nvec;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < mr) {
+        v = __ldg(reinterpret_cast<const float4*>(x + static_cast<size_t>(m0 + r) * K) + (i - r * nvec));
+        if (silu_in) {
+          v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
         }
       }
+      reinterpret_cast<float4*>(sx)[i] = v;
     }
+    __syncthreads();
+    if (n0 < N) {
+      float acc[kLsFeat][kLsRows];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float s = warp_sum(acc[i]);
-      if (lane == 0 && m0 + i < M) {
-        float v = s + (bias ? bias[n] : 0.f);
-        if (silu_out) v = silu_f(v);
-        y[static_cast<size_t>(m0 + i) * N + n] = v;
+      for (int f = 0; f < kLsFeat; ++f)
+#pragma unroll
+        for (int r = 0; r < kLsRows; ++r) acc[f][r] = 0.f;
+      const float4* wr[kLsFeat];
+#pragma unroll
+      for (int f = 0; f < kLsFeat; ++f) wr[f] = reinterpret_cast<const float4*>(w + static_cast<size_t>(min(n0 + f, N - 1)) * K);
+      for (int k = lane; k < nvec; k += 32) {
+        float4 wv[kLsFeat];
+#pragma unroll
+        for (int f = 0; f < kLsFeat; ++f) wv[f] = __ldg(wr[f] + k);
+#pragma unroll
+        for (int r = 0; r < kLsRows; ++r) {
+          const float4 xv = reinterpret_cast<const float4*>(sx)[r * nvec + k];
+#pragma unroll
+          for (int f = 0; f < kLsFeat; ++f)
+            acc[f][r] = fmaf(wv[f].x, xv.x, fmaf(wv[f].y, xv.y, fmaf(wv[f].z, xv.z, fmaf(wv[f].w, xv.w, acc[f][r]))));
+        }
       }
+#pragma unroll
+      for (int f = 0; f < kLsFeat; ++f)
+#pragma unroll
+        for (int r = 0; r < kLsRows; ++r) {
+          const float sacc = warp_sum(acc[f][r]);
+          if (lane == ((f * kLsRows + r) & 31)) acc[f][r] = sacc;   // lane (f*16+r)%32 keeps output (f, r)
+        }
+      // each lane now owns two outputs: (f, r) and (f + 2, r) with f*16 + r == lane
+#pragma unroll
+      for (int f = 0; f < kLsFeat; ++f)
+#pragma unroll
+        for (int r = 0; r < kLsRows; ++r)
+          if (lane == ((f * kLsRows + r) & 31) && r < mr && n0 + f < N) {
+            float v = acc[f][r] + (bias ? bias[n0 + f] : 0.f);
+            if (silu_out) v = silu_f(v);
+            y[static_cast<size_t>(m0 + r) * N + n0 + f] = v;
+          }
     }
   }
 }
@@ -269,9 +341,21 @@ extern "C" int af_conv_in(const float* x_nchw, const float* w, const float* bias
                           int W, int Cout, cudaStream_t stream) {
   AF_CHECK_ARG(x_nchw && w && y_nhwc, "af_conv_in: null pointer");
   AF_CHECK_ARG(Cin == 4, "af_conv_in: Cin=%d unsupported (4)", Cin);
-  dim3 grid((W + 15) / 16, H, B);
-  const int threads = Cout >= 320 ? 320 : ((Cout + 31) / 32) * 32;
-  conv_in_kernel<4><<<grid, threads, 0, stream>>>(x_nchw, w, bias, y_nhwc, B, H, W, Cout);
+  AF_CHECK_ARG(Cout % 4 == 0 && Cout >= 32 && Cout <= 1280, "af_conv_in: Cout=%d unsupported", Cout);
+  const int cq = Cout / 4;
+  int groups = 320 / cq;                       // pixel groups per block; must divide 32 with >= 8 pixels each
+  if (groups > 4) groups = 4;
+  if (groups == 3) groups = 2;
+  if (groups < 1) groups = 1;
+  const int threads = ((groups * cq + 31) / 32) * 32;
+  const size_t smem = (static_cast<size_t>(36) * Cout + 4 * 3 * 34) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    AF_CUDA(cudaFuncSetAttribute(conv_in_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  dim3 grid((W + 31) / 32, H, B);
+  conv_in_kernel<4><<<grid, threads, smem, stream>>>(x_nchw, w, bias, y_nhwc, B, H, W, Cout);
   AF_LAUNCH_CHECK("conv_in_kernel");
   return 0;
 }
@@ -297,6 +381,14 @@ extern "C" int af_conv_out(const void* x_nhwc_bf16, const float* w_packed, const
   return 0;
 }
 
+extern "C" int af_nhwc_to_nchw(const float* x_nhwc, float* y_nchw, int B, int HW, int Cp, int Cout, cudaStream_t stream) {
+  AF_CHECK_ARG(x_nhwc && y_nchw && B > 0 && HW > 0, "af_nhwc_to_nchw: bad args");
+  AF_CHECK_ARG(Cp % 4 == 0 && Cout >= 1 && Cout <= 4 && Cout <= Cp, "af_nhwc_to_nchw: Cp=%d Cout=%d unsupported", Cp, Cout);
+  nhwc_to_nchw_kernel<<<grid_for(static_cast<size_t>(B) * HW, 256), 256, 0, stream>>>(x_nhwc, y_nchw, B, HW, Cp, Cout);
+  AF_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+  return 0;
+}
+
 extern "C" int af_timestep_embedding(const float* t, float* out, int B, int dim, cudaStream_t stream) {
   AF_CHECK_ARG(t && out && B > 0 && dim >= 2, "af_timestep_embedding: bad args");
   const int n = B * (dim / 2);
@@ -309,7 +401,14 @@ extern "C" int af_linear_small(const float* x, const float* w, const float* bias
                                int silu_in, int silu_out, cudaStream_t stream) {
   AF_CHECK_ARG(x && w && y, "af_linear_small: null pointer");
   AF_CHECK_ARG(M > 0 && N > 0 && K > 0 && K % 4 == 0, "af_linear_small: M=%d N=%d K=%d (K%%4)", M, N, K);
-  linear_small_kernel<<<(N + 7) / 8, 256, 0, stream>>>(x, w, bias, y, M, N, K, silu_in, silu_out);
+  const size_t smem = static_cast<size_t>(kLsRows) * K * sizeof(float);
+  AF_CHECK_ARG(smem <= 200 * 1024, "af_linear_small: K=%d too large", K);
+  static size_t configured = 0;
+  if (smem > configured) {
+    AF_CUDA(cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  linear_small_kernel<<<(N + 8 * kLsFeat - 1) / (8 * kLsFeat), 256, smem, stream>>>(x, w, bias, y, M, N, K, silu_in, silu_out);
   AF_LAUNCH_CHECK("linear_small_kernel");
   return 0;
 }

@@ -16,115 +16,143 @@ namespace af {
 constexpr int kGroups = 32;
 
 // ---------------------------------------------------------------------------------------------
-// pass 1: partial (sum, sumsq) per (sample, chunk, group)
-// grid = (chunks, B); block = 256.  Thread t owns channel quad (t % cq) and strides over pixels.
+// Statistics come in ONE format everywhere: per-channel partial sums
+//     stats[(b * slots + slot) * C + c] = (sum, sum of squares) over the pixels of `slot`
+// written either by the epilogue of the GEMM / conv that produced the tensor (gemm_tc.cu, one slot per 32 output
+// rows) or by gn_stats_kernel below (tensors that no tensor-core kernel produced).  gn_finalize_kernel folds
+// them into (mean, rstd) per (sample, group) in a fixed order - no floating-point atomics anywhere, results are
+// bit-reproducible run to run - and gn_apply_kernel makes the single normalising pass over the data.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x0, int C0,
-                                                       const float* __restrict__ x1, int C1, int HW, int chunks,
-                                                       float* __restrict__ partial /* [B, chunks, 32, 2] */) {
-  // Deterministic: every thread parks its per-channel partials in shared memory and one thread per group
-  // sums them in a fixed order (no floating-point atomics anywhere in the GroupNorm path).
-  extern __shared__ float s_part[];  // [slots][8]: 4 channel sums, 4 channel sums of squares
-  const int C = C0 + C1;
+// grid = (slots, B); block = 256.  Thread t owns channel quad (t % cq) and strides over the slot's pixels.
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int C, int HW, int slots,
+                                                       float* __restrict__ stats /* [B, slots, C, 2] */) {
+  extern __shared__ float s_part[];  // [lanes][cq][8]: 4 channel sums, 4 channel sums of squares
   const int cq = C >> 2;             // channel quads per pixel
-  const int cpg = C / kGroups;
   const int b = blockIdx.y;
-  const int chunk = blockIdx.x;
-  const int pix_per_chunk = (HW + chunks - 1) / chunks;
-  const int p_begin = chunk * pix_per_chunk;
-  const int p_end = min(HW, p_begin + pix_per_chunk);
+  const int slot = blockIdx.x;
+  const int pix_per_slot = (HW + slots - 1) / slots;
+  const int p_begin = slot * pix_per_slot;
+  const int p_end = min(HW, p_begin + pix_per_slot);
   const bool narrow = cq <= 256;
-  const int ppb = narrow ? 256 / cq : 1;          // pixels handled per block iteration
-  const int slots = narrow ? ppb * cq : cq;
+  const int ppb = narrow ? 256 / cq : 1;          // pixel lanes per block iteration
 
-  auto accumulate = [&](int q, int p_first, int p_step, int slot) {
+  auto accumulate = [&](int q, int p_first, int p_step, int dst) {
     float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-    const int c = q * 4;
-    const float* src;
-    int cs, off;
-    if (c < C0) { src = x0; cs = C0; off = c; } else { src = x1; cs = C1; off = c - C0; }
-    const float* base = src + static_cast<size_t>(b) * HW * cs + off;
+    const float* base = x + static_cast<size_t>(b) * HW * C + q * 4;
     auto acc = [&](const float4& v) {
-      s[0] += v.x; ss[0] += v.x * v.x;
-      s[1] += v.y; ss[1] += v.y * v.y;
-      s[2] += v.z; ss[2] += v.z * v.z;
-      s[3] += v.w; ss[3] += v.w * v.w;
+      s[0] += v.x; ss[0] = fmaf(v.x, v.x, ss[0]);
+      s[1] += v.y; ss[1] = fmaf(v.y, v.y, ss[1]);
+      s[2] += v.z; ss[2] = fmaf(v.z, v.z, ss[2]);
+      s[3] += v.w; ss[3] = fmaf(v.w, v.w, ss[3]);
     };
     int p = p_first;
     // four independent 16-byte loads in flight per thread (memory-level parallelism), fixed summation order
     for (; p + 3 * p_step < p_end; p += 4 * p_step) {
-      const float4 v0 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p) * cs));
-      const float4 v1 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + p_step) * cs));
-      const float4 v2 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + 2 * p_step) * cs));
-      const float4 v3 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + 3 * p_step) * cs));
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p) * C));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + p_step) * C));
+      const float4 v2 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + 2 * p_step) * C));
+      const float4 v3 = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p + 3 * p_step) * C));
       acc(v0); acc(v1); acc(v2); acc(v3);
     }
-    for (; p < p_end; p += p_step) acc(__ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p) * cs)));
+    for (; p < p_end; p += p_step) acc(__ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(p) * C)));
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      s_part[slot * 8 + e] = s[e];
-      s_part[slot * 8 + 4 + e] = ss[e];
+      s_part[dst * 8 + e] = s[e];
+      s_part[dst * 8 + 4 + e] = ss[e];
     }
   };
 
   if (narrow) {
-    // a fixed thread always sees the same channel quad; slot = pixel lane * cq + quad == threadIdx.x
-    if (threadIdx.x < slots) accumulate(threadIdx.x % cq, p_begin + threadIdx.x / cq, ppb, threadIdx.x);
+    if (threadIdx.x < ppb * cq) accumulate(threadIdx.x % cq, p_begin + threadIdx.x / cq, ppb, threadIdx.x);
   } else {
     for (int q = threadIdx.x; q < cq; q += 256) accumulate(q, p_begin, 1, q);
   }
   __syncthreads();
-  if (threadIdx.x < kGroups) {
-    const int g = threadIdx.x;
-    float s = 0.f, ss = 0.f;
-    const int lanes = narrow ? ppb : 1;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      const int q = c >> 2, e = c & 3;
-      for (int l = 0; l < lanes; ++l) {
-        s += s_part[(l * cq + q) * 8 + e];
-        ss += s_part[(l * cq + q) * 8 + 4 + e];
+  float* out = stats + (static_cast<size_t>(b) * slots + slot) * C * 2;
+  const int lanes = narrow ? ppb : 1;
+  for (int q = threadIdx.x; q < cq; q += 256) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int l = 0; l < lanes; ++l) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        s[e] += s_part[(l * cq + q) * 8 + e];
+        ss[e] += s_part[(l * cq + q) * 8 + 4 + e];
       }
     }
-    float* o = partial + ((static_cast<size_t>(b) * chunks + chunk) * kGroups + g) * 2;
-    o[0] = s;
-    o[1] = ss;
+    float4* o = reinterpret_cast<float4*>(out + q * 8);
+    o[0] = make_float4(s[0], ss[0], s[1], ss[1]);
+    o[1] = make_float4(s[2], ss[2], s[3], ss[3]);
+  }
+}
+
+// grid = (32 groups, B); block = 128.  mean_rstd[b][g] = (mean, rstd) over the group's channels of [x0 | x1].
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ st0, int C0, int slots0,
+                                                          const float* __restrict__ st1, int C1, int slots1, int HW,
+                                                          float eps, float* __restrict__ mean_rstd) {
+  __shared__ float red[2][128];
+  const int C = C0 + C1;
+  const int cpg = C / kGroups;
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int c_lo = g * cpg, c_hi = c_lo + cpg;
+  float s = 0.f, ss = 0.f;
+  // source 0 part of the group
+  {
+    const int lo = min(c_lo, C0), hi = min(c_hi, C0), w = hi - lo;
+    const float2* base = reinterpret_cast<const float2*>(st0) + static_cast<size_t>(b) * slots0 * C0;
+    for (int i = threadIdx.x; i < w * slots0; i += 128) {
+      const int sl = i / w, c = lo + (i - sl * w);
+      const float2 v = __ldg(base + static_cast<size_t>(sl) * C0 + c);
+      s += v.x; ss += v.y;
+    }
+  }
+  if (C1 > 0) {
+    const int lo = max(c_lo, C0) - C0, hi = max(c_hi, C0) - C0, w = hi - lo;
+    const float2* base = reinterpret_cast<const float2*>(st1) + static_cast<size_t>(b) * slots1 * C1;
+    for (int i = threadIdx.x; i < w * slots1; i += 128) {
+      const int sl = i / w, c = lo + (i - sl * w);
+      const float2 v = __ldg(base + static_cast<size_t>(sl) * C1 + c);
+      s += v.x; ss += v.y;
+    }
+  }
+  red[0][threadIdx.x] = s;
+  red[1][threadIdx.x] = ss;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {   // fixed-shape tree: deterministic
+    if (threadIdx.x < o) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + o];
+      red[1][threadIdx.x] += red[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float n = static_cast<float>(HW) * cpg;
+    const float mean = red[0][0] / n;
+    const float var = fmaxf(red[1][0] / n - mean * mean, 0.f);
+    mean_rstd[(static_cast<size_t>(b) * kGroups + g) * 2] = mean;
+    mean_rstd[(static_cast<size_t>(b) * kGroups + g) * 2 + 1] = rsqrtf(var + eps);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass 2: y = silu?((x - mean) * rstd * gamma + beta) -> bf16 (optionally also a raw bf16 copy of x)
+// y = silu?((x - mean) * rstd * gamma + beta) -> bf16 (optionally also a raw bf16 copy of x)
 // grid = (blocks_per_sample, B); block = 256
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x0, int C0,
-                                                       const float* __restrict__ x1, int C1, int HW, int chunks,
-                                                       const float* __restrict__ partial,
+                                                       const float* __restrict__ x1, int C1, int HW,
+                                                       const float* __restrict__ mean_rstd,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       float eps, int silu, __nv_bfloat16* __restrict__ y,
+                                                       int silu, __nv_bfloat16* __restrict__ y,
                                                        __nv_bfloat16* __restrict__ raw) {
   extern __shared__ float s_ab[];  // [2*C]: scale a[c], shift b[c]
   const int C = C0 + C1;
   const int cpg = C / kGroups;
   const int b = blockIdx.y;
-  __shared__ float s_mean[kGroups], s_rstd[kGroups];
-  if (threadIdx.x < kGroups) {
-    float s = 0.f, ss = 0.f;
-    const float* pp = partial + (static_cast<size_t>(b) * chunks * kGroups + threadIdx.x) * 2;
-    for (int k = 0; k < chunks; ++k) {
-      s += pp[static_cast<size_t>(k) * kGroups * 2];
-      ss += pp[static_cast<size_t>(k) * kGroups * 2 + 1];
-    }
-    const float n = static_cast<float>(HW) * cpg;
-    const float mean = s / n;
-    const float var = fmaxf(ss / n - mean * mean, 0.f);
-    s_mean[threadIdx.x] = mean;
-    s_rstd[threadIdx.x] = rsqrtf(var + eps);
-  }
-  __syncthreads();
+  const float2* mr = reinterpret_cast<const float2*>(mean_rstd) + static_cast<size_t>(b) * kGroups;
   for (int c = threadIdx.x; c < C; c += 256) {
-    const int g = c / cpg;
-    const float a = s_rstd[g] * gamma[c];
+    const float2 m = __ldg(mr + c / cpg);
+    const float a = m.y * gamma[c];
     s_ab[c] = a;
-    s_ab[C + c] = beta[c] - s_mean[g] * a;
+    s_ab[C + c] = beta[c] - m.x * a;
   }
   __syncthreads();
 
@@ -146,10 +174,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
     return xb1 + static_cast<size_t>(p) * C1 + (c - C0);
   };
   auto emit = [&](uint32_t i, int c, const float4& v) {
-    float o0 = v.x * s_ab[c] + s_ab[C + c];
-    float o1 = v.y * s_ab[c + 1] + s_ab[C + c + 1];
-    float o2 = v.z * s_ab[c + 2] + s_ab[C + c + 2];
-    float o3 = v.w * s_ab[c + 3] + s_ab[C + c + 3];
+    const float4 a = *reinterpret_cast<const float4*>(s_ab + c);
+    const float4 sh = *reinterpret_cast<const float4*>(s_ab + C + c);
+    float o0 = fmaf(v.x, a.x, sh.x);
+    float o1 = fmaf(v.y, a.y, sh.y);
+    float o2 = fmaf(v.z, a.z, sh.z);
+    float o3 = fmaf(v.w, a.w, sh.w);
     if (silu) {
       o0 = silu_f(o0); o1 = silu_f(o1); o2 = silu_f(o2); o3 = silu_f(o3);
     }
@@ -237,39 +267,85 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 
 using namespace af;
 
-extern "C" size_t af_groupnorm_workspace_bytes(int B) {
-  return static_cast<size_t>(B) * AF_GN_MAX_CHUNKS * kGroups * 2 * sizeof(float);
+static int gn_default_slots(int B, int HW) {
+  // enough blocks to fill the machine, few enough that the finalize pass stays cheap
+  int slots = (8 * num_sms() + B - 1) / B;
+  if (slots > HW / 16) slots = HW / 16;   // keep >= 16 pixels per block
+  if (slots > AF_GN_MAX_CHUNKS) slots = AF_GN_MAX_CHUNKS;
+  if (slots > HW) slots = HW;
+  if (slots < 1) slots = 1;
+  return slots;
 }
 
-extern "C" int af_groupnorm_silu(const float* x0, int C0, const float* x1, int C1, int B, int HW,
-                                 const float* gamma, const float* beta, float eps, int silu, void* y_bf16,
-                                 void* raw_bf16, float* workspace, cudaStream_t stream) {
-  AF_CHECK_ARG(x0 && gamma && beta && y_bf16 && workspace, "af_groupnorm_silu: null pointer");
-  const int C = C0 + C1;
-  AF_CHECK_ARG(B > 0 && HW > 0 && C0 > 0 && C1 >= 0, "af_groupnorm_silu: bad sizes");
-  AF_CHECK_ARG(C % 32 == 0 && C0 % 4 == 0 && C1 % 4 == 0, "af_groupnorm_silu: C0=%d C1=%d need C%%32==0, quads", C0, C1);
-  AF_CHECK_ARG(C1 == 0 || x1 != nullptr, "af_groupnorm_silu: x1 null with C1=%d", C1);
-  AF_CHECK_ARG(C <= 5120, "af_groupnorm_silu: C=%d too large", C);
-  // enough chunks to fill the machine, few enough that pass 2 sums them cheaply
-  int chunks = (8 * num_sms() + B - 1) / B;
-  if (chunks > HW / 16) chunks = HW / 16;   // keep >= 16 pixels per block
-  if (chunks > AF_GN_MAX_CHUNKS) chunks = AF_GN_MAX_CHUNKS;
-  if (chunks > HW) chunks = HW;
-  if (chunks < 1) chunks = 1;
+extern "C" int af_groupnorm_stats_slots(int B, int HW) { return gn_default_slots(B, HW); }
+
+extern "C" size_t af_groupnorm_workspace_bytes(int B, int C) {
+  // per-channel partials of both sources (<= AF_GN_MAX_CHUNKS slots) + (mean, rstd) per (sample, group)
+  return (static_cast<size_t>(B) * AF_GN_MAX_CHUNKS * C * 2 + static_cast<size_t>(B) * kGroups * 2) * sizeof(float);
+}
+
+extern "C" int af_groupnorm_stats(const float* x, int C, int B, int HW, float* stats, int slots, cudaStream_t stream) {
+  AF_CHECK_ARG(x && stats, "af_groupnorm_stats: null pointer");
+  AF_CHECK_ARG(B > 0 && HW > 0 && C > 0 && C % 4 == 0 && C <= 5120, "af_groupnorm_stats: bad sizes B=%d HW=%d C=%d", B, HW, C);
+  AF_CHECK_ARG(slots >= 1 && slots <= HW, "af_groupnorm_stats: slots=%d", slots);
   const int cq = C / 4;
-  const size_t stats_smem = static_cast<size_t>(cq <= 256 ? (256 / cq) * cq : cq) * 8 * sizeof(float);
-  gn_stats_kernel<<<dim3(chunks, B), 256, stats_smem, stream>>>(x0, C0, x1, C1, HW, chunks, workspace);
+  const size_t smem = static_cast<size_t>(cq <= 256 ? (256 / cq) * cq : cq) * 8 * sizeof(float);
+  gn_stats_kernel<<<dim3(slots, B), 256, smem, stream>>>(x, C, HW, slots, stats);
   AF_LAUNCH_CHECK("gn_stats_kernel");
+  return 0;
+}
+
+extern "C" int af_groupnorm_finalize(const float* stats0, int C0, int slots0, const float* stats1, int C1, int slots1,
+                                     int B, int HW, float eps, float* mean_rstd, cudaStream_t stream) {
+  AF_CHECK_ARG(stats0 && mean_rstd, "af_groupnorm_finalize: null pointer");
+  AF_CHECK_ARG(B > 0 && HW > 0 && C0 > 0 && C1 >= 0 && (C0 + C1) % 32 == 0 && slots0 > 0, "af_groupnorm_finalize: bad sizes");
+  AF_CHECK_ARG(C1 == 0 || (stats1 && slots1 > 0), "af_groupnorm_finalize: second source needs stats");
+  gn_finalize_kernel<<<dim3(kGroups, B), 128, 0, stream>>>(stats0, C0, slots0, stats1, C1, slots1, HW, eps, mean_rstd);
+  AF_LAUNCH_CHECK("gn_finalize_kernel");
+  return 0;
+}
+
+extern "C" int af_groupnorm_apply(const float* x0, int C0, const float* x1, int C1, int B, int HW,
+                                  const float* mean_rstd, const float* gamma, const float* beta, int silu,
+                                  void* y_bf16, void* raw_bf16, cudaStream_t stream) {
+  AF_CHECK_ARG(x0 && mean_rstd && gamma && beta && y_bf16, "af_groupnorm_apply: null pointer");
+  const int C = C0 + C1;
+  AF_CHECK_ARG(B > 0 && HW > 0 && C0 > 0 && C1 >= 0, "af_groupnorm_apply: bad sizes");
+  AF_CHECK_ARG(C % 32 == 0 && C0 % 4 == 0 && C1 % 4 == 0, "af_groupnorm_apply: C0=%d C1=%d need C%%32==0, quads", C0, C1);
+  AF_CHECK_ARG(C1 == 0 || x1 != nullptr, "af_groupnorm_apply: x1 null with C1=%d", C1);
+  AF_CHECK_ARG(C <= 5120, "af_groupnorm_apply: C=%d too large", C);
   const size_t total = static_cast<size_t>(HW) * (C / 4);
   int blocks = static_cast<int>((total + 256 * 8 - 1) / (256 * 8));
   const int cap = (16 * num_sms() + B - 1) / B;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   gn_apply_kernel<<<dim3(blocks, B), 256, 2 * C * sizeof(float), stream>>>(
-      x0, C0, x1, C1, HW, chunks, workspace, gamma, beta, eps, silu, static_cast<__nv_bfloat16*>(y_bf16),
+      x0, C0, x1, C1, HW, mean_rstd, gamma, beta, silu, static_cast<__nv_bfloat16*>(y_bf16),
       static_cast<__nv_bfloat16*>(raw_bf16));
   AF_LAUNCH_CHECK("gn_apply_kernel");
   return 0;
+}
+
+// all-in-one: statistics pass(es) + finalize + apply
+extern "C" int af_groupnorm_silu(const float* x0, int C0, const float* x1, int C1, int B, int HW,
+                                 const float* gamma, const float* beta, float eps, int silu, void* y_bf16,
+                                 void* raw_bf16, float* workspace, cudaStream_t stream) {
+  AF_CHECK_ARG(x0 && gamma && beta && y_bf16 && workspace, "af_groupnorm_silu: null pointer");
+  AF_CHECK_ARG(B > 0 && HW > 0 && C0 > 0 && C1 >= 0 && C0 % 4 == 0 && C1 % 4 == 0, "af_groupnorm_silu: bad sizes");
+  const int slots = gn_default_slots(B, HW);
+  float* st0 = workspace;
+  float* st1 = st0 + static_cast<size_t>(B) * slots * C0 * 2;
+  float* mr = workspace + static_cast<size_t>(B) * AF_GN_MAX_CHUNKS * (C0 + C1) * 2;
+  int rc = af_groupnorm_stats(x0, C0, B, HW, st0, slots, stream);
+  if (rc) return rc;
+  if (C1 > 0) {
+    AF_CHECK_ARG(x1 != nullptr, "af_groupnorm_silu: x1 null with C1=%d", C1);
+    rc = af_groupnorm_stats(x1, C1, B, HW, st1, slots, stream);
+    if (rc) return rc;
+  }
+  rc = af_groupnorm_finalize(st0, C0, slots, C1 > 0 ? st1 : nullptr, C1, slots, B, HW, eps, mr, stream);
+  if (rc) return rc;
+  return af_groupnorm_apply(x0, C0, x1, C1, B, HW, mr, gamma, beta, silu, y_bf16, raw_bf16, stream);
 }
 
 extern "C" int af_layernorm(const float* x, long long rows, int C, const float* gamma, const float* beta, float eps,

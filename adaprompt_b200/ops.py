@@ -35,7 +35,7 @@ def _chk(t: torch.Tensor, dtype, name: str) -> None:
 
 
 def _epilogue(out: torch.Tensor, bias=None, rowbias=None, rows_per_group=0, residual=None, geglu=False,
-              ldo: int = 0, ldr: int = 0) -> AfEpilogue:
+              ldo: int = 0, ldr: int = 0, gn_stats: Optional[torch.Tensor] = None) -> AfEpilogue:
     # rowbias may be a column slice of a wider [groups, total] matrix: its row stride is passed along
     ep = AfEpilogue()
     if bias is not None:
@@ -60,13 +60,18 @@ def _epilogue(out: torch.Tensor, bias=None, rowbias=None, rows_per_group=0, resi
     else:
         raise ValueError(f"out dtype {out.dtype} unsupported")
     ep.geglu = 1 if geglu else 0
+    if gn_stats is not None:
+        _chk(gn_stats, torch.float32, "gn_stats")
+    ep.gn_stats = _p(gn_stats)
     return ep
 
 
 def gemm(a0: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, *, a1: Optional[torch.Tensor] = None,
          bias=None, rowbias=None, rows_per_group=0, residual=None, geglu=False, ldo: int = 0, ldr: int = 0,
-         bn: int = 0, M: Optional[int] = None, lda0: Optional[int] = None, K0: Optional[int] = None) -> torch.Tensor:
-    """out[M, N] = [a0 | a1] @ wt^T (+ fused epilogue).  a*: bf16 [M, K*]; wt: bf16 [N, K0+K1]."""
+         bn: int = 0, M: Optional[int] = None, lda0: Optional[int] = None, K0: Optional[int] = None,
+         gn_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M, N] = [a0 | a1] @ wt^T (+ fused epilogue).  a*: bf16 [M, K*]; wt: bf16 [N, K0+K1].
+    gn_stats: fp32 [ceil(M/128)*4, N, 2] per-32-row (sum, sumsq) of the written values (see gn_stats_for_rows)."""
     lib = _lib.load()
     _chk(wt, torch.bfloat16, "wt")
     if a0.dtype != torch.bfloat16 or not a0.is_cuda:
@@ -81,14 +86,15 @@ def gemm(a0: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, *, a1: Optional[
     N = int(wt.shape[0])
     if int(wt.shape[1]) != K0 + K1:
         raise ValueError(f"wt K={wt.shape[1]} != K0+K1={K0 + K1}")
-    ep = _epilogue(out, bias, rowbias, rows_per_group, residual, geglu, ldo, ldr)
+    ep = _epilogue(out, bias, rowbias, rows_per_group, residual, geglu, ldo, ldr, gn_stats)
     rc = lib.af_gemm_bf16(a0.data_ptr(), lda0, K0, _p(a1), lda1, K1, wt.data_ptr(), M, N, byref(ep), bn, _stream())
     _lib.check(rc, "af_gemm_bf16")
     return out
 
 
 def conv3x3(x0: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, *, x1: Optional[torch.Tensor] = None, stride=1,
-            bias=None, rowbias=None, residual=None, bn: int = 0) -> torch.Tensor:
+            bias=None, rowbias=None, residual=None, bn: int = 0,
+            gn_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x*: bf16 NHWC [B,H,W,C*]; wt: bf16 [Cout, 3, 3, C0+C1]; out: [B,Ho,Wo,Cout] fp32|bf16."""
     lib = _lib.load()
     _chk(x0, torch.bfloat16, "x0")
@@ -101,7 +107,7 @@ def conv3x3(x0: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, *, x1: Option
     Cout = int(wt.shape[0])
     if wt.numel() != Cout * 9 * (C0 + C1):
         raise ValueError("conv3x3 weight shape mismatch")
-    ep = _epilogue(out, bias, rowbias, 0, residual)
+    ep = _epilogue(out, bias, rowbias, 0, residual, gn_stats=gn_stats)
     rc = lib.af_conv3x3_bf16(x0.data_ptr(), C0, _p(x1), C1, wt.data_ptr(), B, H, W, Cout, stride, byref(ep), bn,
                              _stream())
     _lib.check(rc, "af_conv3x3_bf16")
@@ -123,11 +129,78 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Ten
     return out
 
 
-def _gn_workspace(B: int, device) -> torch.Tensor:
-    key = (B, device)
+class GNStats:
+    """Per-channel partial GroupNorm statistics of one fp32 NHWC tensor: buf fp32 [B, slots, C, 2]
+    (include/adaface_b200.h, "Statistics format").  Produced by a GEMM / conv epilogue or by groupnorm_stats."""
+
+    __slots__ = ("buf", "slots", "C")
+
+    def __init__(self, buf: torch.Tensor, slots: int, C: int):
+        self.buf, self.slots, self.C = buf, slots, C
+
+
+def gn_stats_for_gemm(B: int, HW: int, C: int, device) -> Optional[GNStats]:
+    """Statistics buffer a GEMM epilogue can fill for an output of B*HW rows (None: geometry unsupported)."""
+    if HW % 32 != 0:
+        return None
+    rows32 = (B * HW + 127) // 128 * 4
+    return GNStats(torch.empty(rows32 * C * 2, dtype=torch.float32, device=device), HW // 32, C)
+
+
+def gn_stats_for_conv(B: int, Ho: int, Wo: int, C: int, device) -> Optional[GNStats]:
+    slots = _lib.load().af_conv3x3_gn_slots(Ho, Wo)
+    if slots <= 0:
+        return None
+    return GNStats(torch.empty(B * slots * C * 2, dtype=torch.float32, device=device), slots, C)
+
+
+def groupnorm_stats(x: torch.Tensor) -> GNStats:
+    """Stand-alone statistics pass for a tensor no tensor-core kernel produced."""
+    lib = _lib.load()
+    _chk(x, torch.float32, "x")
+    B, C = int(x.shape[0]), int(x.shape[-1])
+    HW = x.numel() // (B * C)
+    slots = lib.af_groupnorm_stats_slots(B, HW)
+    st = GNStats(torch.empty(B * slots * C * 2, dtype=torch.float32, device=x.device), slots, C)
+    rc = lib.af_groupnorm_stats(x.data_ptr(), C, B, HW, st.buf.data_ptr(), slots, _stream())
+    _lib.check(rc, "af_groupnorm_stats")
+    return st
+
+
+def groupnorm_apply(x0: torch.Tensor, st0: GNStats, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool,
+                    out: torch.Tensor, *, x1: Optional[torch.Tensor] = None, st1: Optional[GNStats] = None,
+                    raw: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(32) [+SiLU] of [x0 | x1] from precomputed statistics: finalize (tiny) + ONE pass over the data."""
+    lib = _lib.load()
+    _chk(x0, torch.float32, "x0")
+    _chk(out, torch.bfloat16, "out")
+    B, C0 = int(x0.shape[0]), int(x0.shape[-1])
+    HW = x0.numel() // (B * C0)
+    C1 = 0
+    if x1 is not None:
+        _chk(x1, torch.float32, "x1")
+        C1 = int(x1.shape[-1])
+        if st1 is None or st1.C != C1:
+            raise ValueError("groupnorm_apply: x1 needs matching statistics")
+    if st0.C != C0:
+        raise ValueError("groupnorm_apply: statistics / tensor channel mismatch")
+    if raw is not None:
+        _chk(raw, torch.bfloat16, "raw")
+    mr = torch.empty(B * 64, dtype=torch.float32, device=x0.device)
+    rc = lib.af_groupnorm_finalize(st0.buf.data_ptr(), C0, st0.slots, st1.buf.data_ptr() if C1 else None, C1,
+                                   st1.slots if C1 else 0, B, HW, float(eps), mr.data_ptr(), _stream())
+    _lib.check(rc, "af_groupnorm_finalize")
+    rc = lib.af_groupnorm_apply(x0.data_ptr(), C0, _p(x1), C1, B, HW, mr.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                1 if silu else 0, out.data_ptr(), _p(raw), _stream())
+    _lib.check(rc, "af_groupnorm_apply")
+    return out
+
+
+def _gn_workspace(B: int, C: int, device) -> torch.Tensor:
+    key = (B, C, device)
     ws = _gn_ws.get(key)
     if ws is None:
-        n = _lib.load().af_groupnorm_workspace_bytes(B)
+        n = _lib.load().af_groupnorm_workspace_bytes(B, C)
         ws = torch.empty(n // 4, dtype=torch.float32, device=device)
         _gn_ws[key] = ws
     return ws
@@ -136,7 +209,8 @@ def _gn_workspace(B: int, device) -> torch.Tensor:
 def groupnorm_silu(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool,
                    out: torch.Tensor, *, x1: Optional[torch.Tensor] = None, raw: Optional[torch.Tensor] = None,
                    workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x*: fp32 NHWC [B, H, W, C*] (or [B, HW, C*]); out: bf16 [B, HW, C0+C1]."""
+    """x*: fp32 NHWC [B, H, W, C*] (or [B, HW, C*]); out: bf16 [B, HW, C0+C1].  All-in-one (statistics passes
+    included); the UNet fast path uses groupnorm_apply with producer-side statistics instead."""
     lib = _lib.load()
     _chk(x0, torch.float32, "x0")
     _chk(out, torch.bfloat16, "out")
@@ -148,7 +222,7 @@ def groupnorm_silu(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, ep
         C1 = int(x1.shape[-1])
     if raw is not None:
         _chk(raw, torch.bfloat16, "raw")
-    ws = workspace if workspace is not None else _gn_workspace(B, x0.device)
+    ws = workspace if workspace is not None else _gn_workspace(B, C0 + C1, x0.device)
     rc = lib.af_groupnorm_silu(x0.data_ptr(), C0, _p(x1), C1, B, HW, gamma.data_ptr(), beta.data_ptr(), float(eps),
                                1 if silu else 0, out.data_ptr(), _p(raw), ws.data_ptr(), _stream())
     _lib.check(rc, "af_groupnorm_silu")
@@ -187,6 +261,17 @@ def conv_out(x_nhwc: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, o
     rc = lib.af_conv_out(x_nhwc.data_ptr(), w_packed.data_ptr(), _p(bias), out_nchw.data_ptr(), B, H, W, C,
                          int(w_packed.shape[0]), _stream())
     _lib.check(rc, "af_conv_out")
+    return out_nchw
+
+
+def nhwc_to_nchw(x_nhwc: torch.Tensor, out_nchw: torch.Tensor) -> torch.Tensor:
+    """x fp32 [B,H,W,Cp] -> out fp32 [B,Cout,H,W] (first Cout <= 4 channels)."""
+    lib = _lib.load()
+    _chk(x_nhwc, torch.float32, "x")
+    _chk(out_nchw, torch.float32, "out")
+    B, H, W, Cp = (int(v) for v in x_nhwc.shape)
+    rc = lib.af_nhwc_to_nchw(x_nhwc.data_ptr(), out_nchw.data_ptr(), B, H * W, Cp, int(out_nchw.shape[1]), _stream())
+    _lib.check(rc, "af_nhwc_to_nchw")
     return out_nchw
 
 

@@ -47,6 +47,29 @@ def _nhwc(x: torch.Tensor) -> torch.Tensor:
     return x.float().permute(0, 2, 3, 1).contiguous()
 
 
+class Act:
+    """An fp32 NHWC activation of the residual stream plus the per-channel GroupNorm partial statistics its
+    producer's epilogue wrote (ops.GNStats) - the GroupNorm that consumes it never re-reads it for statistics.
+    Tensors no tensor-core kernel produced get a stand-alone statistics pass on first use (cached: skip tensors
+    are normalised twice, openaimodel.py:982,1019)."""
+
+    __slots__ = ("t", "st")
+
+    def __init__(self, t: torch.Tensor, st=None):
+        self.t, self.st = t, st
+
+    def stats(self):
+        if self.st is None:
+            self.st = ops.groupnorm_stats(self.t)
+        return self.st
+
+
+def _conv_out_act(B, Ho, Wo, C, device):
+    out = torch.empty(B, Ho, Wo, C, dtype=torch.float32, device=device)
+    st = ops.gn_stats_for_conv(B, Ho, Wo, C, device)
+    return out, st
+
+
 def _nchw(x: torch.Tensor) -> torch.Tensor:
     return x.permute(0, 3, 1, 2).contiguous()
 
@@ -77,12 +100,13 @@ class Upsample(PackedModule):
         assert C == self.channels
         up = torch.empty(B, 2 * H, 2 * W, C, dtype=torch.bfloat16, device=x.device)
         ops.upsample2x_cast(x, up)
-        out = torch.empty(B, 2 * H, 2 * W, self.out_channels, dtype=torch.float32, device=x.device)
-        return ops.conv3x3(up, pk["w"], out, bias=pk["b"])
+        out, st = _conv_out_act(B, 2 * H, 2 * W, self.out_channels, x.device)
+        ops.conv3x3(up, pk["w"], out, bias=pk["b"], gn_stats=st.buf if st else None)
+        return Act(out, st)
 
     def forward(self, x):
         assert x.shape[1] == self.channels
-        return _nchw(self._run(_nhwc(x)))
+        return _nchw(self._run(_nhwc(x)).t)
 
 
 class Downsample(PackedModule):
@@ -106,12 +130,13 @@ class Downsample(PackedModule):
         B, H, W, C = x.shape
         assert C == self.channels
         xb = ops.cast_bf16(x)
-        out = torch.empty(B, H // 2, W // 2, self.out_channels, dtype=torch.float32, device=x.device)
-        return ops.conv3x3(xb, pk["w"], out, stride=2, bias=pk["b"])
+        out, st = _conv_out_act(B, H // 2, W // 2, self.out_channels, x.device)
+        ops.conv3x3(xb, pk["w"], out, stride=2, bias=pk["b"], gn_stats=st.buf if st else None)
+        return Act(out, st)
 
     def forward(self, x):
         assert x.shape[1] == self.channels
-        return _nchw(self._run(_nhwc(x)))
+        return _nchw(self._run(_nhwc(x)).t)
 
 
 class ResBlock(TimestepBlock, PackedModule):
@@ -154,13 +179,15 @@ class ResBlock(TimestepBlock, PackedModule):
             pk["bs"] = f(self.skip_connection.bias)
         return pk
 
-    def _run(self, parts, emb_rows: torch.Tensor) -> torch.Tensor:
-        """parts: (x,) or (h, skip) fp32 NHWC tensors whose channel concat is the block input
-        (openaimodel.py:1019 torch.cat is never materialised in fp32); emb_rows fp32 [B, Cout] =
-        emb_layers(emb) (may be a column slice of the UNet-level batched projection)."""
+    def _run(self, parts, emb_rows: torch.Tensor) -> "Act":
+        """parts: (x,) or (h, skip) Acts whose channel concat is the block input (openaimodel.py:1019 torch.cat is
+        never materialised in fp32); emb_rows fp32 [B, Cout] = emb_layers(emb) (may be a column slice of the
+        UNet-level batched projection)."""
         pk = self.packed()
-        x0 = parts[0]
-        x1 = parts[1] if len(parts) > 1 else None
+        a0 = parts[0]
+        a1 = parts[1] if len(parts) > 1 else None
+        x0 = a0.t
+        x1 = a1.t if a1 is not None else None
         B, H, W, C0 = x0.shape
         Cin = C0 + (x1.shape[-1] if x1 is not None else 0)
         assert Cin == self.channels, (Cin, self.channels)
@@ -169,19 +196,22 @@ class ResBlock(TimestepBlock, PackedModule):
         has_skip_conv = "ws" in pk
         y = torch.empty(B, H, W, Cin, dtype=torch.bfloat16, device=dev)
         raw = torch.empty(B, H, W, Cin, dtype=torch.bfloat16, device=dev) if has_skip_conv else None
-        ops.groupnorm_silu(x0, pk["gn1_w"], pk["gn1_b"], pk["eps1"], True, y, x1=x1, raw=raw)     # :205-207
-        h1 = torch.empty(B, H, W, Cout, dtype=torch.float32, device=dev)
-        ops.conv3x3(y, pk["w1"], h1, bias=pk["b1"], rowbias=emb_rows)                              # :208,:277
+        ops.groupnorm_apply(x0, a0.stats(), pk["gn1_w"], pk["gn1_b"], pk["eps1"], True, y, x1=x1,
+                            st1=a1.stats() if a1 is not None else None, raw=raw)                   # :205-207
+        h1, st1 = _conv_out_act(B, H, W, Cout, dev)
+        ops.conv3x3(y, pk["w1"], h1, bias=pk["b1"], rowbias=emb_rows, gn_stats=st1.buf if st1 else None)  # :208,:277
         y2 = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=dev)
-        ops.groupnorm_silu(h1, pk["gn2_w"], pk["gn2_b"], pk["eps2"], True, y2)                     # :229-231
+        ops.groupnorm_apply(h1, st1 if st1 else ops.groupnorm_stats(h1), pk["gn2_w"], pk["gn2_b"], pk["eps2"], True,
+                            y2)                                                                    # :229-231
         if has_skip_conv:
             res = torch.empty(B, H, W, Cout, dtype=torch.float32, device=dev)
             ops.gemm(raw.reshape(B * H * W, Cin), pk["ws"], res, bias=pk["bs"])                    # :245
         else:
             assert x1 is None
             res = x0
-        out = torch.empty(B, H, W, Cout, dtype=torch.float32, device=dev)
-        return ops.conv3x3(y2, pk["w2"], out, bias=pk["b2"], residual=res)                          # :234,:279
+        out, sto = _conv_out_act(B, H, W, Cout, dev)
+        ops.conv3x3(y2, pk["w2"], out, bias=pk["b2"], residual=res, gn_stats=sto.buf if sto else None)  # :234,:279
+        return Act(out, sto)
 
     def emb_proj(self, emb: torch.Tensor) -> torch.Tensor:
         pk = self.packed()
@@ -190,7 +220,7 @@ class ResBlock(TimestepBlock, PackedModule):
 
     def forward(self, x, emb):
         """Reference signature: x [B,C,H,W], emb [B, emb_channels] -> [B,Cout,H,W]."""
-        return _nchw(self._run((_nhwc(x),), self.emb_proj(emb)))
+        return _nchw(self._run((Act(_nhwc(x)),), self.emb_proj(emb)).t)
 
     _forward = forward
 
@@ -209,17 +239,17 @@ class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
         return x
 
     def _run(self, parts, emb_rows_of, context, mask):
-        """NHWC fast path.  parts: tuple of fp32 NHWC tensors (channel concat = input)."""
+        """NHWC fast path.  parts: tuple of Acts (channel concat = input) -> Act."""
         x = parts
         for layer in self:
             if isinstance(layer, ResBlock):
                 x = (layer._run(x, emb_rows_of(layer)),)
             elif isinstance(layer, SpatialTransformer):
-                x = (layer._run(x[0], context, mask),)
+                x = (layer._run_act(x[0], context, mask),)
             elif isinstance(layer, (Upsample, Downsample)):
-                x = (layer._run(x[0]),)
+                x = (layer._run(x[0].t),)
             elif isinstance(layer, ConvIn):
-                x = (layer._run(x[0]),)
+                x = (Act(layer._run(x[0].t)),)
             else:
                 raise NotImplementedError(type(layer))
         return x[0]
@@ -389,7 +419,22 @@ class UNetModel(PackedModule):
                 "emb_b": torch.cat([f(rb.emb_layers[1].bias) for rb in rbs], 0).contiguous(),
                 "emb_offs": offs, "emb_total": o,
                 "out_gn_w": f(self.out[0].weight), "out_gn_b": f(self.out[0].bias), "out_eps": float(self.out[0].eps),
-                "out_w": f(self.out[2].weight.detach().permute(0, 2, 3, 1)), "out_b": f(self.out[2].bias)}
+                "out_w": self._pad_out_conv(self.out[2].weight.detach()), "out_b": self._pad_out_bias(self.out[2].bias.detach())}
+
+    @staticmethod
+    def _pad_out_conv(w_oihw):
+        """UNetModel.out[-1] (openaimodel.py:696): Cout 4 -> 8 zero rows so the conv runs on the tensor cores."""
+        co = w_oihw.shape[0]
+        wp = torch.zeros((co + 7) // 8 * 8, *w_oihw.shape[1:], dtype=w_oihw.dtype, device=w_oihw.device)
+        wp[:co] = w_oihw
+        return pack_conv3x3(wp)
+
+    @staticmethod
+    def _pad_out_bias(b):
+        co = b.shape[0]
+        bp = torch.zeros((co + 7) // 8 * 8, dtype=torch.float32, device=b.device)
+        bp[:co] = b.float()
+        return bp
 
     def invalidate_packed(self):
         super().invalidate_packed()
@@ -523,7 +568,7 @@ class UNetModel(PackedModule):
             return rows[:, o:o + n]
 
         hs = []
-        h = x
+        h = Act(x)
         layer_idx = 0
         for module in self.input_blocks:                                                   # :977-990
             h = module._run((h,), emb_rows_of, kvs.get(layer_idx), img_mask)
@@ -534,8 +579,11 @@ class UNetModel(PackedModule):
         for module in self.output_blocks:                                                  # :1016-1029
             h = module._run((h, hs.pop()), emb_rows_of, kvs.get(layer_idx), img_mask)
             layer_idx += 1
-        B, H, W, C = h.shape
-        y = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=h.device)
-        ops.groupnorm_silu(h, pk["out_gn_w"], pk["out_gn_b"], pk["out_eps"], True, y)      # :693-695
-        out = torch.empty(B, self.out_channels, H, W, dtype=torch.float32, device=h.device)
-        return ops.conv_out(y, pk["out_w"], pk["out_b"], out)                               # :696,:1052
+        B, H, W, C = h.t.shape
+        dev = h.t.device
+        y = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=dev)
+        ops.groupnorm_apply(h.t, h.stats(), pk["out_gn_w"], pk["out_gn_b"], pk["out_eps"], True, y)   # :693-695
+        o8 = torch.empty(B, H, W, pk["out_w"].shape[0], dtype=torch.float32, device=dev)
+        ops.conv3x3(y, pk["out_w"], o8, bias=pk["out_b"], bn=64)                                       # :696,:1052
+        out = torch.empty(B, self.out_channels, H, W, dtype=torch.float32, device=dev)
+        return ops.nhwc_to_nchw(o8, out)

@@ -51,7 +51,11 @@ typedef struct af_epilogue {
   long long ldo;          /* row pitch in elements; <= 0: N (N/2 for geglu) */
   int out_dtype;          /* AF_DTYPE_F32 | AF_DTYPE_BF16 */
   int geglu;              /* 1: GEGLU (attention.py:32-39): weight rows packed per 256-col tile as [128 value | 128 gate];
-                             out[:, j] = (x.Wv_j + bv_j) * gelu_erf(x.Wg_j + bg_j), N/2 bf16 output columns */
+                             out[:, j] = (x.Wv_j + bv_j) * gelu(x.Wg_j + bg_j), N/2 bf16 output columns */
+  float* gn_stats;        /* NULL, or [slots][N][2] fp32: per-channel (sum, sum of squares) of the values written, one
+                             slot per 32 consecutive output rows (GEMM: slot = row / 32, rows-per-sample must be a
+                             multiple of 32; conv: af_conv3x3_gn_slots() slots per sample).  Feeds af_groupnorm_finalize
+                             so the GroupNorm that consumes this tensor never re-reads it for statistics. */
 } af_epilogue;
 
 /* D[M,N] = [A0 | A1][M, K0+K1] . Wt[N, K0+K1]^T, bf16 operands (row-major, K contiguous), fp32 accumulate.
@@ -66,6 +70,8 @@ int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* A1, long lo
  * (n, oh, ow) row-major.  Replaces nn.Conv2d 3x3 at openaimodel.py:155 (stride 2), :208, :234, :120-122. */
 int af_conv3x3_bf16(const void* X0, int C0, const void* X1, int C1, const void* Wt, int B, int H, int W, int Cout,
                     int stride, const af_epilogue* ep, int bn_hint, af_stream_t stream);
+/* statistic slots per sample that af_conv3x3_bf16 writes for an Ho x Wo output (0: unsupported geometry). */
+int af_conv3x3_gn_slots(int Ho, int Wo);
 
 /* Flash attention, 8-head SD-1.5 geometry (d in {40,80,160}); replaces attention.py:198-242.
  * Q [B,Nq,ldq], K [B,Nk,ldk] bf16 with head h at column h*DP (DP = 48 for d = 40, zero padded, else d);
@@ -79,8 +85,20 @@ int af_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk
 /* GroupNorm(32) over the channel concat [x0 | x1] of fp32 NHWC tensors, optional SiLU, bf16 output
  * [B, HW, C0+C1]; optional raw bf16 copy of the concat (operand of the 1x1 skip conv).
  * Replaces GroupNorm32+SiLU (util.py:217-219; openaimodel.py:205-207,229-231,693-695) and Normalize
- * (attention.py:71-72,325).  workspace: af_groupnorm_workspace_bytes(B) bytes. */
-size_t af_groupnorm_workspace_bytes(int B);
+ * (attention.py:71-72,325).
+ * Statistics format (one per source tensor): stats[(b*slots + slot)*C + c] = (sum, sum of squares) over the pixels
+ * of `slot` - written by the epilogue of the GEMM / conv that produced the tensor (af_epilogue.gn_stats) or by
+ * af_groupnorm_stats.  af_groupnorm_finalize -> mean_rstd [B,32,2]; af_groupnorm_apply makes the one data pass.
+ * af_groupnorm_silu = stats + finalize + apply with workspace af_groupnorm_workspace_bytes(B, C0+C1).
+ * All reductions run in a fixed order (bit-reproducible). */
+size_t af_groupnorm_workspace_bytes(int B, int C);
+int af_groupnorm_stats_slots(int B, int HW);
+int af_groupnorm_stats(const float* x, int C, int B, int HW, float* stats, int slots, af_stream_t stream);
+int af_groupnorm_finalize(const float* stats0, int C0, int slots0, const float* stats1, int C1, int slots1, int B,
+                          int HW, float eps, float* mean_rstd, af_stream_t stream);
+int af_groupnorm_apply(const float* x0, int C0, const float* x1, int C1, int B, int HW, const float* mean_rstd,
+                       const float* gamma, const float* beta, int silu, void* y_bf16, void* raw_bf16,
+                       af_stream_t stream);
 int af_groupnorm_silu(const float* x0, int C0, const float* x1, int C1, int B, int HW, const float* gamma,
                       const float* beta, float eps, int silu, void* y_bf16, void* raw_bf16, float* workspace,
                       af_stream_t stream);
@@ -95,6 +113,10 @@ int af_conv_in(const float* x_nchw, const float* w /*[Cout,Cin,3,3]*/, const flo
                int H, int W, int Cout, af_stream_t stream);
 int af_conv_out(const void* x_nhwc_bf16, const float* w_packed /*[Cout,3,3,C]*/, const float* bias, float* y_nchw,
                 int B, int H, int W, int C, int Cout, af_stream_t stream);
+
+/* NHWC fp32 [B,HW,Cp] -> NCHW fp32 [B,Cout,HW] (first Cout <= 4 of the Cp padded channels): public layout of the
+ * UNet output after the last conv ran on the tensor cores with Cout padded 4 -> 8 (openaimodel.py:696,1052). */
+int af_nhwc_to_nchw(const float* x_nhwc, float* y_nchw, int B, int HW, int Cp, int Cout, af_stream_t stream);
 
 /* timestep_embedding (util.py:154-174): out[b] = [cos(t_b f) | sin(t_b f)], fp32. */
 int af_timestep_embedding(const float* t, float* out, int B, int dim, af_stream_t stream);
@@ -113,6 +135,30 @@ int af_upsample2x_cast(const float* x_nhwc, void* y_bf16, int B, int H, int W, i
 int af_cfg_ddim_update(const float* x, const float* eps, int has_uncond, const float* noise, const float* coef_table,
                        const int* step_idx, float* x_prev, float* pred_x0, long long n, af_stream_t stream);
 int af_advance_step(int* step_idx, const float* t_table, float* t_buf, int B, int num_steps, af_stream_t stream);
+
+/* ---- conditioning path: CLIP text transformer pieces and AdaFace token splicing (once per prompt) ---- */
+
+/* Causal / full multi-head attention for short sequences (CLIP text: 12 heads x 64, L <= 77).  qkv bf16 [B*L, ldq]:
+ * q at column 0, k at k_off, v at v_off; head h of q at h*64.  mult > 1 = CLIPAttentionMKV
+ * (adaface/arc2face_models.py:87-173): token t contributes `mult` keys/values, key (t, r) of head h at column
+ * k_off + (h*mult + r)*64, masked like token t.  scale multiplies q (head_dim^-1/2).  out bf16 [B*L, ldo]. */
+int af_attention_small(const void* qkv, long long ldq, int k_off, int v_off, void* out, long long ldo, int B,
+                       int heads, int L, int mult, float scale, int causal, af_stream_t stream);
+/* out[r,:] = table[ids[r],:] (token_embedding lookup, exact copies; ids are int64 as torch.long). */
+int af_gather_rows(const float* table, const long long* ids, float* out, long long rows, int dim, int vocab,
+                   af_stream_t stream);
+/* x[b,t,:] += pos[t,:] (CLIPTextEmbeddings position add, modules.py:213-221). */
+int af_add_pos(float* x, const float* pos, long long rows, int L, int dim, af_stream_t stream);
+/* first[r] = first position of `token` in ids[r,:] or -1 (embedding_manager.py:1359,1368). */
+int af_find_first_token(const long long* ids, int rows, int L, long long token, int* first, af_stream_t stream);
+/* dst[r, start[r]+k, :] = src[src_index ? src_index[r] : r, k, :], k < K, rows with start[r] < 0 untouched
+ * (embedding_manager.py:1516-1562; adaface/util.py:107,184).  Exact row copies: bit-exact by construction. */
+int af_splice_rows(float* dst, const float* src, const int* start, const int* src_index, int rows, int L, int K,
+                   int dim, af_stream_t stream);
+/* out = w0*a + w1*b (+ w2*c): weighted sum of the last hidden states (arc2face_models.py:236-246, modules.py:361-368),
+ * evaluated as ((w0*a + w1*b) + w2*c) like (stack * w).sum(0). */
+int af_weighted_sum(const float* a, const float* b, const float* c, float w0, float w1, float w2, float* out,
+                    long long n, af_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -33,6 +33,14 @@ if case in ("all", "res"):
     gemm_case(65536, 320, 320, True, True)
 if case in ("all", "geglu"):
     gemm_case(65536, 2560, 320, False, False, geglu=True)
+if case == "f32":
+    gemm_case(65536, 320, 320, False, True)
+if case == "qk":
+    gemm_case(65536, 768, 320, False, False)
+if case == "conv8":
+    conv_case(16, 8, 1280, 1280)
+if case == "conv64":
+    conv_case(16, 64, 320, 320)
 if case == "all":
     gemm_case(65536, 320, 320, False, False)
     gemm_case(65536, 320, 320, False, True)

@@ -21,7 +21,13 @@ t = torch.full((B,), 501.0, device="cuda")
 ctx = torch.randn(16 * B, 77, 768, generator=g).cuda()
 extra = {"use_layerwise_context": True, "use_conv_attn_kernel_size": -1, "placeholder2indices": None,
          "is_training": False}
+import json
 with torch.no_grad():
+    with _lib.profile() as prof:
+        unet(x, t, context=ctx, extra_info=dict(extra))
+    prof.summary()
+    json.dump([(r[0], r[5], _lib.KERNELS_PER_CALL[r[0]], r[3], r[4]) for r in prof.records],
+              open("gpurun_out/step_calls.json", "w"))
     for i in range(reps):
         n0 = _lib.TRACE.count
         eps = unet(x, t, context=ctx, extra_info=dict(extra))

@@ -368,3 +368,111 @@ def test_cfg_ddim_update_bit_exact():
     ref = a_prev_f.sqrt() * pred + dir_xt + sig * torch.zeros_like(xc)
     assert torch.equal(p0.cpu(), pred)
     assert torch.equal(xp.cpu(), ref)
+
+
+# ------------------------------------------------------------------------------------------------ fused GN statistics
+def _group_stats_ref(x, eps):
+    """x fp32 [B, HW, C] -> (mean, rstd) [B, 32] in float64."""
+    B, HW, C = x.shape
+    g = x.double().reshape(B, HW, 32, C // 32)
+    mean = g.mean(dim=(1, 3))
+    var = g.var(dim=(1, 3), unbiased=False)
+    return mean, (var + eps).rsqrt()
+
+
+@pytest.mark.parametrize("B,HW,N,K,res", [(2, 4096, 320, 320, True), (3, 256, 1280, 640, False), (2, 64, 1280, 1280, True),
+                                           (1, 1024, 640, 2560, True)])
+def test_gemm_epilogue_gn_stats(B, HW, N, K, res):
+    """Statistics written by the GEMM epilogue == statistics of the tensor it wrote; GroupNorm from them."""
+    from adaprompt_b200 import ops
+    M = B * HW
+    a = _rand(M, K, seed=1, dtype=torch.bfloat16)
+    w = _rand(N, K, seed=2, scale=K ** -0.5, dtype=torch.bfloat16)
+    bias = _rand(N, seed=3)
+    r = _rand(M, N, seed=4) if res else None
+    out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    st = ops.gn_stats_for_gemm(B, HW, N, DEV)
+    assert st is not None
+    ops.gemm(a, w, out, bias=bias, residual=r, gn_stats=st.buf)
+    part = st.buf.reshape(-1, N, 2)[: M // 32].double()
+    rows = out.double().reshape(M // 32, 32, N)
+    assert torch.allclose(part[..., 0], rows.sum(1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(part[..., 1], (rows * rows).sum(1), rtol=1e-5, atol=1e-3)
+    gamma = 1 + 0.1 * _rand(N, seed=5)
+    beta = 0.1 * _rand(N, seed=6)
+    y = torch.empty(B, HW, N, device=DEV, dtype=torch.bfloat16)
+    ops.groupnorm_apply(out.reshape(B, HW, N), st, gamma, beta, 1e-5, True, y)
+    ref = F.silu(F.group_norm(out.reshape(B, HW, N).permute(0, 2, 1), 32, gamma, beta, 1e-5).permute(0, 2, 1))
+    assert _rel(y, ref) < 3e-3
+    # bit-reproducible
+    st2 = ops.gn_stats_for_gemm(B, HW, N, DEV)
+    out2 = torch.empty_like(out)
+    ops.gemm(a, w, out2, bias=bias, residual=r, gn_stats=st2.buf)
+    assert torch.equal(st.buf[: (M // 32) * N * 2], st2.buf[: (M // 32) * N * 2])
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [(2, 64, 64, 320, 320, 1), (3, 8, 8, 1280, 1280, 1), (2, 32, 32, 640, 640, 2),
+                                                    (1, 24, 24, 640, 320, 1), (2, 16, 16, 1280, 640, 1)])
+def test_conv_epilogue_gn_stats_feed_groupnorm(B, H, W, Cin, Cout, stride):
+    from adaprompt_b200 import ops
+    from adaprompt_b200.packing import pack_conv3x3
+    x = _rand(B, H, W, Cin, seed=1, dtype=torch.bfloat16)
+    w = _rand(Cout, Cin, 3, 3, seed=2, scale=(9 * Cin) ** -0.5).to(torch.bfloat16)
+    bias = _rand(Cout, seed=3)
+    Ho, Wo = H // stride, W // stride
+    out = torch.empty(B, Ho, Wo, Cout, device=DEV, dtype=torch.float32)
+    st = ops.gn_stats_for_conv(B, Ho, Wo, Cout, DEV)
+    assert st is not None
+    ops.conv3x3(x, pack_conv3x3(w), out, stride=stride, bias=bias, gn_stats=st.buf)
+    tot = st.buf.reshape(B, st.slots, Cout, 2).double().sum(1)
+    flat = out.double().reshape(B, Ho * Wo, Cout)
+    assert torch.allclose(tot[..., 0], flat.sum(1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(tot[..., 1], (flat * flat).sum(1), rtol=1e-5, atol=1e-3)
+    # two-source GroupNorm: conv-produced statistics for x0, stand-alone statistics pass for x1
+    x1 = _rand(B, Ho, Wo, 320, seed=7) - 0.5
+    C = Cout + 320
+    gamma = 1 + 0.1 * _rand(C, seed=5)
+    beta = 0.1 * _rand(C, seed=6)
+    y = torch.empty(B, Ho * Wo, C, device=DEV, dtype=torch.bfloat16)
+    raw = torch.empty_like(y)
+    ops.groupnorm_apply(out, st, gamma, beta, 1e-6, False, y, x1=x1, st1=ops.groupnorm_stats(x1), raw=raw)
+    cat = torch.cat([out, x1], -1).reshape(B, Ho * Wo, C)
+    ref = F.group_norm(cat.permute(0, 2, 1), 32, gamma, beta, 1e-6).permute(0, 2, 1)
+    assert _rel(y, ref) < 3e-3
+    assert torch.equal(raw, cat.to(torch.bfloat16))
+
+
+def test_conv_gn_slots_small_images_unsupported():
+    from adaprompt_b200 import ops
+    assert ops.gn_stats_for_conv(2, 4, 4, 1280, DEV) is None      # 16 pixels per sample < one 32-row slot
+    assert ops.gn_stats_for_gemm(2, 16, 1280, DEV) is None
+    assert ops.gn_stats_for_conv(2, 8, 8, 1280, DEV).slots == 2
+
+
+def test_conv_out_tensor_core_path():
+    """UNetModel.out[-1] (320 -> 4) as an implicit GEMM with Cout padded to 8 + NHWC->NCHW."""
+    from adaprompt_b200 import ops
+    from adaprompt_b200.unet import UNetModel
+    B, H, W, C = 2, 64, 64, 320
+    x = _rand(B, H, W, C, seed=1, dtype=torch.bfloat16)
+    w = _rand(4, C, 3, 3, seed=2, scale=(9 * C) ** -0.5).to(torch.bfloat16)
+    bias = _rand(4, seed=3)
+    o8 = torch.empty(B, H, W, 8, device=DEV, dtype=torch.float32)
+    ops.conv3x3(x, UNetModel._pad_out_conv(w.float()), o8, bias=UNetModel._pad_out_bias(bias), bn=64)
+    out = torch.empty(B, 4, H, W, device=DEV, dtype=torch.float32)
+    ops.nhwc_to_nchw(o8, out)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1)
+    assert _rel(out, ref) < 2e-5
+    assert o8[..., 4:].abs().max().item() == 0.0
+
+
+def test_linear_small_many_rows_and_tail_features():
+    from adaprompt_b200 import ops
+    for M, N, K in [(16, 1280, 320), (33, 1286, 1280), (2, 20480, 1280)]:
+        x = _rand(M, K, seed=1)
+        w = _rand(N, K, seed=2, scale=K ** -0.5)
+        b = _rand(N, seed=3)
+        y = torch.empty(M, N, device=DEV)
+        ops.linear_small(x, w, b, y, silu_in=True, silu_out=True)
+        ref = F.silu(F.silu(x).double() @ w.double().t() + b.double()).float()
+        assert _rel(y, ref) < 1e-5
