@@ -30,6 +30,7 @@ class AfEpilogue(Structure):
         ("ldo", c_longlong),
         ("out_dtype", c_int),
         ("geglu", c_int),
+        ("act", c_int),
         ("gn_stats", c_void_p),
     ]
 
@@ -56,6 +57,7 @@ SIGNATURES = {
     "af_groupnorm_silu": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "af_layernorm": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+    "af_layernorm_f32": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
     "af_conv_in": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "af_conv_out": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "af_nhwc_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -110,7 +112,7 @@ KERNELS_PER_CALL = {
     "af_gemm_bf16": 1, "af_conv3x3_bf16": 1, "af_attention_bf16": 1, "af_groupnorm_silu": 3, "af_layernorm": 1,
     "af_groupnorm_stats": 1, "af_groupnorm_finalize": 1, "af_groupnorm_apply": 1, "af_nhwc_to_nchw": 1,
     "af_attention_small": 1, "af_gather_rows": 1, "af_add_pos": 1, "af_find_first_token": 1, "af_splice_rows": 1,
-    "af_weighted_sum": 1,
+    "af_weighted_sum": 1, "af_layernorm_f32": 1,
     "af_conv_in": 1, "af_conv_out": 1, "af_timestep_embedding": 1, "af_linear_small": 1, "af_cast_bf16": 1,
     "af_upsample2x_cast": 1, "af_cfg_ddim_update": 1, "af_advance_step": 1,
 }

@@ -47,6 +47,7 @@ struct GemmParams {
   long long ldo;
   int out_bf16;
   int geglu;               // tile cols [0,BN/2) = value, [BN/2,BN) = gate; writes BN/2 cols
+  int act;                 // 0 none, 1 quick_gelu x*sigmoid(1.702x) on (acc + bias), before the residual add
   float* gn_stats;         // [slots_total][N][2] per-channel (sum, sumsq) over 32-row quarters of the output, or null
   int gn_slots;            // conv: stat slots per sample (= tiles_w * tiles_h * bw * bh / 32)
 };
@@ -78,6 +79,9 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
 }
+
+// QuickGELU of the CLIP text MLP (transformers QuickGELUActivation): x * sigmoid(1.702 x)
+__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
 template <int BN, bool GEGLU>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
@@ -374,8 +378,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           for (int k = 0; k < 8; ++k) {
             const int R = 4 * k + sub;
             const float4 a = *reinterpret_cast<const float4*>(stg + R * 128 + ((cl ^ (R & 7)) << 4));
-            float4 o = make_float4(a.x + b4.x + rs[k].x, a.y + b4.y + rs[k].y, a.z + b4.z + rs[k].z,
-                                   a.w + b4.w + rs[k].w);
+            float4 t4 = make_float4(a.x + b4.x, a.y + b4.y, a.z + b4.z, a.w + b4.w);
+            if (p.act == 1) {
+              t4.x = quick_gelu(t4.x); t4.y = quick_gelu(t4.y); t4.z = quick_gelu(t4.z); t4.w = quick_gelu(t4.w);
+            }
+            float4 o = make_float4(t4.x + rs[k].x, t4.y + rs[k].y, t4.z + rs[k].z, t4.w + rs[k].w);
             if (((valid >> k) & 1u) && col_ok) {
               if (late_rowbias) {
                 const float4 rb = __ldg(reinterpret_cast<const float4*>(
@@ -487,6 +494,8 @@ static int fill_epilogue(GemmParams& p, const af_epilogue* ep, long long default
   p.out_bf16 = ep->out_dtype == AF_DTYPE_BF16;
   p.geglu = ep->geglu;
   p.gn_stats = ep->gn_stats;
+  p.act = ep->act;
+  AF_CHECK_ARG(ep->act == 0 || (ep->act == 1 && !ep->geglu), "epilogue: act %d unsupported", ep->act);
   AF_CHECK_ARG(!ep->gn_stats || (!ep->geglu && (reinterpret_cast<uintptr_t>(ep->gn_stats) & 15) == 0),
                "epilogue: gn_stats needs the generic epilogue and a 16-byte aligned buffer");
   AF_CHECK_ARG(ep->out != nullptr, "epilogue: out is null");

@@ -214,11 +214,11 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
 // ---------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, row held in registers (C <= 2048, C % 128 == 0 not required; C % 4 == 0)
 // ---------------------------------------------------------------------------------------------
-template <int MAXV>  // float4 vectors per lane
+template <int MAXV, bool F32OUT>  // float4 vectors per lane; output bf16 (GEMM operand) or fp32
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long rows, int C,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
-                                                        __nv_bfloat16* __restrict__ y) {
+                                                        void* __restrict__ yv) {
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -249,16 +249,21 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const float rstd = rsqrtf(ss / C + eps);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
-  uint2* yr = reinterpret_cast<uint2*>(y + row * C);
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int k = lane + i * 32;
     if (k < nvec) {
       const float4 g = __ldg(g4 + k), bb = __ldg(b4 + k);
-      uint2 pk;
-      pk.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
-      pk.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
-      yr[k] = pk;
+      const float4 o = make_float4((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y,
+                                   (v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
+      if (F32OUT) {
+        reinterpret_cast<float4*>(static_cast<float*>(yv) + row * C)[k] = o;
+      } else {
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(yv) + row * C)[k] = pk;
+      }
     }
   }
 }
@@ -348,21 +353,32 @@ extern "C" int af_groupnorm_silu(const float* x0, int C0, const float* x1, int C
   return af_groupnorm_apply(x0, C0, x1, C1, B, HW, mr, gamma, beta, silu, y_bf16, raw_bf16, stream);
 }
 
-extern "C" int af_layernorm(const float* x, long long rows, int C, const float* gamma, const float* beta, float eps,
-                            void* y_bf16, cudaStream_t stream) {
-  AF_CHECK_ARG(x && gamma && beta && y_bf16, "af_layernorm: null pointer");
+template <bool F32OUT>
+static int launch_layernorm(const float* x, long long rows, int C, const float* gamma, const float* beta, float eps,
+                            void* y, cudaStream_t stream) {
+  AF_CHECK_ARG(x && gamma && beta && y, "af_layernorm: null pointer");
   AF_CHECK_ARG(rows > 0 && C > 0 && C % 4 == 0 && C <= 2048, "af_layernorm: rows=%lld C=%d (need C%%4==0, C<=2048)", rows, C);
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
   const int nvec = C / 4;
   if (nvec <= 3 * 32) {
-    layernorm_kernel<3><<<grid, 256, 0, stream>>>(x, rows, C, gamma, beta, eps, static_cast<__nv_bfloat16*>(y_bf16));
+    layernorm_kernel<3, F32OUT><<<grid, 256, 0, stream>>>(x, rows, C, gamma, beta, eps, y);
   } else if (nvec <= 5 * 32) {
-    layernorm_kernel<5><<<grid, 256, 0, stream>>>(x, rows, C, gamma, beta, eps, static_cast<__nv_bfloat16*>(y_bf16));
+    layernorm_kernel<5, F32OUT><<<grid, 256, 0, stream>>>(x, rows, C, gamma, beta, eps, y);
   } else if (nvec <= 10 * 32) {
-    layernorm_kernel<10><<<grid, 256, 0, stream>>>(x, rows, C, gamma, beta, eps, static_cast<__nv_bfloat16*>(y_bf16));
+    layernorm_kernel<10, F32OUT><<<grid, 256, 0, stream>>>(x, rows, C, gamma, beta, eps, y);
   } else {
-    layernorm_kernel<16><<<grid, 256, 0, stream>>>(x, rows, C, gamma, beta, eps, static_cast<__nv_bfloat16*>(y_bf16));
+    layernorm_kernel<16, F32OUT><<<grid, 256, 0, stream>>>(x, rows, C, gamma, beta, eps, y);
   }
   AF_LAUNCH_CHECK("layernorm_kernel");
   return 0;
+}
+
+extern "C" int af_layernorm(const float* x, long long rows, int C, const float* gamma, const float* beta, float eps,
+                            void* y_bf16, cudaStream_t stream) {
+  return launch_layernorm<false>(x, rows, C, gamma, beta, eps, y_bf16, stream);
+}
+
+extern "C" int af_layernorm_f32(const float* x, long long rows, int C, const float* gamma, const float* beta, float eps,
+                                float* y, cudaStream_t stream) {
+  return launch_layernorm<true>(x, rows, C, gamma, beta, eps, y, stream);
 }

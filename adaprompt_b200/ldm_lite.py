@@ -38,9 +38,17 @@ class LatentDiffusionLite(nn.Module):
     apply_model / q_sample, with the SD-1.5 'linear' schedule (v1-inference-ada.yaml:5-9)."""
 
     def __init__(self, unet: nn.Module = None, timesteps=1000, linear_start=0.00085, linear_end=0.012,
-                 beta_schedule="linear", scale_factor=0.18215, parameterization="eps"):
+                 beta_schedule="linear", scale_factor=0.18215, parameterization="eps", cond_stage_model=None,
+                 embedding_manager=None):
         super().__init__()
         self.model = DiffusionWrapper(unet if unet is not None else UNetModel(**SD15_UNET_CONFIG))
+        self.cond_stage_model = cond_stage_model      # clip_text.FrozenCLIPEmbedder (ddpm.py:756)
+        self.embedding_manager = embedding_manager    # embedding_manager.EmbeddingManagerLite (ddpm.py:793)
+        self.use_layerwise_embedding = True           # v1-inference-ada.yaml:19
+        self.N_CA_LAYERS = 16                         # ddpm.py:150
+        self.empty_context = None
+        self.compel_cfg_weight_level_range = None
+        self.apply_compel_cfg_prob = 0
         self.parameterization = parameterization
         self.scale_factor = scale_factor
         self.register_schedule(beta_schedule, timesteps, linear_start, linear_end)
@@ -70,6 +78,37 @@ class LatentDiffusionLite(nn.Module):
         a = self.sqrt_alphas_cumprod[t].reshape(-1, *((1,) * (x_start.dim() - 1)))
         b = self.sqrt_one_minus_alphas_cumprod[t].reshape(-1, *((1,) * (x_start.dim() - 1)))
         return a * x_start + b * noise
+
+    def get_learned_conditioning(self, cond_in, zs_clip_features=None, zs_id_embs=None,
+                                 zs_out_id_embs_scale_range=(1.0, 1.0), randomize_clip_weights=False,
+                                 apply_arc2face_inverse_embs=False, apply_arc2face_embs=False, embman_iter_type=None):
+        """ddpm.py:970-1085, inference path: prompts (or token ids) -> (static_prompt_embedding [16*B, 77, 768],
+        cond_in, extra_info).  The uncond prompt passes no zs features and so reuses none."""
+        if randomize_clip_weights or apply_arc2face_inverse_embs or apply_arc2face_embs:
+            raise NotImplementedError("training / Arc2Face-evaluation conditioning variants")
+        if self.cond_stage_model is None or self.embedding_manager is None:
+            raise RuntimeError("LatentDiffusionLite: cond_stage_model / embedding_manager are not set")
+        if zs_clip_features is not None or zs_id_embs is not None:
+            self.embedding_manager.set_zs_image_features(zs_clip_features, zs_id_embs,
+                                                         zs_out_id_embs_scale_range=zs_out_id_embs_scale_range)
+            apply_compel_cfg_prob = 0                                                               # :994
+        else:
+            apply_compel_cfg_prob = self.apply_compel_cfg_prob
+        self.embedding_manager.iter_type = embman_iter_type or "recon_iter"                         # :1008
+        static_prompt_embedding = self.cond_stage_model.encode(cond_in, embedding_manager=self.embedding_manager)  # :1011
+        import copy
+        extra_info = {                                                                              # :1065-1076
+            "use_layerwise_context": self.use_layerwise_embedding,
+            "use_conv_attn_kernel_size": getattr(self.embedding_manager, "use_conv_attn_kernel_size", -1),
+            "placeholder2indices": copy.copy(self.embedding_manager.placeholder2indices),
+            "prompt_emb_mask": copy.copy(self.embedding_manager.prompt_emb_mask),
+            "is_training": self.embedding_manager.training,
+            "compel_cfg_weight_level_range": self.compel_cfg_weight_level_range,
+            "apply_compel_cfg_prob": apply_compel_cfg_prob,
+            "empty_context": self.empty_context,
+            "capture_distill_attn": False,
+        }
+        return (static_prompt_embedding, cond_in, extra_info)                                       # :1078
 
     def refresh_conditioning(self, cond, batch: int):
         """Hook for the CUDA-graph sampler: (re)project the conditioning tuple's context through the 16

@@ -35,7 +35,7 @@ def _chk(t: torch.Tensor, dtype, name: str) -> None:
 
 
 def _epilogue(out: torch.Tensor, bias=None, rowbias=None, rows_per_group=0, residual=None, geglu=False,
-              ldo: int = 0, ldr: int = 0, gn_stats: Optional[torch.Tensor] = None) -> AfEpilogue:
+              ldo: int = 0, ldr: int = 0, gn_stats: Optional[torch.Tensor] = None, act: int = 0) -> AfEpilogue:
     # rowbias may be a column slice of a wider [groups, total] matrix: its row stride is passed along
     ep = AfEpilogue()
     if bias is not None:
@@ -60,6 +60,7 @@ def _epilogue(out: torch.Tensor, bias=None, rowbias=None, rows_per_group=0, resi
     else:
         raise ValueError(f"out dtype {out.dtype} unsupported")
     ep.geglu = 1 if geglu else 0
+    ep.act = int(act)
     if gn_stats is not None:
         _chk(gn_stats, torch.float32, "gn_stats")
     ep.gn_stats = _p(gn_stats)
@@ -69,8 +70,8 @@ def _epilogue(out: torch.Tensor, bias=None, rowbias=None, rows_per_group=0, resi
 def gemm(a0: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, *, a1: Optional[torch.Tensor] = None,
          bias=None, rowbias=None, rows_per_group=0, residual=None, geglu=False, ldo: int = 0, ldr: int = 0,
          bn: int = 0, M: Optional[int] = None, lda0: Optional[int] = None, K0: Optional[int] = None,
-         gn_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[M, N] = [a0 | a1] @ wt^T (+ fused epilogue).  a*: bf16 [M, K*]; wt: bf16 [N, K0+K1].
+         gn_stats: Optional[torch.Tensor] = None, act: int = 0) -> torch.Tensor:
+    """out[M, N] = [a0 | a1] @ wt^T (+ fused epilogue).  act=1: quick_gelu on (acc + bias).  a*: bf16 [M, K*]; wt: bf16 [N, K0+K1].
     gn_stats: fp32 [ceil(M/128)*4, N, 2] per-32-row (sum, sumsq) of the written values (see gn_stats_for_rows)."""
     lib = _lib.load()
     _chk(wt, torch.bfloat16, "wt")
@@ -86,7 +87,7 @@ def gemm(a0: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, *, a1: Optional[
     N = int(wt.shape[0])
     if int(wt.shape[1]) != K0 + K1:
         raise ValueError(f"wt K={wt.shape[1]} != K0+K1={K0 + K1}")
-    ep = _epilogue(out, bias, rowbias, rows_per_group, residual, geglu, ldo, ldr, gn_stats)
+    ep = _epilogue(out, bias, rowbias, rows_per_group, residual, geglu, ldo, ldr, gn_stats, act)
     rc = lib.af_gemm_bf16(a0.data_ptr(), lda0, K0, _p(a1), lda1, K1, wt.data_ptr(), M, N, byref(ep), bn, _stream())
     _lib.check(rc, "af_gemm_bf16")
     return out
@@ -230,10 +231,17 @@ def groupnorm_silu(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, ep
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out: torch.Tensor) -> torch.Tensor:
+    """out bf16 (GEMM operand) or fp32 (CLIP final_layer_norm)."""
     lib = _lib.load()
     _chk(x, torch.float32, "x")
-    _chk(out, torch.bfloat16, "out")
     C = int(x.shape[-1])
+    if out.dtype == torch.float32:
+        _chk(out, torch.float32, "out")
+        rc = lib.af_layernorm_f32(x.data_ptr(), x.numel() // C, C, gamma.data_ptr(), beta.data_ptr(), float(eps),
+                                  out.data_ptr(), _stream())
+        _lib.check(rc, "af_layernorm_f32")
+        return out
+    _chk(out, torch.bfloat16, "out")
     rc = lib.af_layernorm(x.data_ptr(), x.numel() // C, C, gamma.data_ptr(), beta.data_ptr(), float(eps),
                           out.data_ptr(), _stream())
     _lib.check(rc, "af_layernorm")
@@ -338,3 +346,83 @@ def advance_step(step_idx: torch.Tensor, t_table: torch.Tensor, t_buf: torch.Ten
     rc = lib.af_advance_step(step_idx.data_ptr(), t_table.data_ptr(), t_buf.data_ptr(), int(t_buf.shape[0]),
                              int(num_steps), _stream())
     _lib.check(rc, "af_advance_step")
+
+
+# ---------------------------------------------------------------------------------------------------
+# conditioning path (text.cu)
+# ---------------------------------------------------------------------------------------------------
+def attention_small(qkv: torch.Tensor, out: torch.Tensor, *, B: int, heads: int, L: int, k_off: int, v_off: int,
+                    mult: int = 1, scale: float = 0.125, causal: bool = True) -> torch.Tensor:
+    """qkv bf16 [B*L, ldq] (q | k | v column blocks, keys/values [head][r][64] for MKV) -> out bf16 [B*L, heads*64]."""
+    lib = _lib.load()
+    _chk(qkv, torch.bfloat16, "qkv")
+    _chk(out, torch.bfloat16, "out")
+    rc = lib.af_attention_small(qkv.data_ptr(), int(qkv.stride(0)), int(k_off), int(v_off), out.data_ptr(),
+                                int(out.stride(0)), B, heads, L, mult, float(scale), int(causal), _stream())
+    _lib.check(rc, "af_attention_small")
+    return out
+
+
+def gather_rows(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[..., :] = table[ids[...], :] (fp32, exact copies)."""
+    lib = _lib.load()
+    _chk(table, torch.float32, "table")
+    _chk(ids, torch.int64, "ids")
+    if out is None:
+        out = torch.empty(*ids.shape, table.shape[1], dtype=torch.float32, device=table.device)
+    rc = lib.af_gather_rows(table.data_ptr(), ids.data_ptr(), out.data_ptr(), ids.numel(), int(table.shape[1]),
+                            int(table.shape[0]), _stream())
+    _lib.check(rc, "af_gather_rows")
+    return out
+
+
+def add_pos(x: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+    """x [B, L, D] += pos[:L] in place."""
+    lib = _lib.load()
+    _chk(x, torch.float32, "x")
+    _chk(pos, torch.float32, "pos")
+    L, D = int(x.shape[-2]), int(x.shape[-1])
+    rc = lib.af_add_pos(x.data_ptr(), pos.data_ptr(), x.numel() // D, L, D, _stream())
+    _lib.check(rc, "af_add_pos")
+    return x
+
+
+def find_first_token(ids: torch.Tensor, token: int) -> torch.Tensor:
+    """ids int64 [R, L] -> int32 [R]: first position of `token` per row or -1."""
+    lib = _lib.load()
+    _chk(ids, torch.int64, "ids")
+    R, L = int(ids.shape[0]), int(ids.shape[1])
+    out = torch.empty(R, dtype=torch.int32, device=ids.device)
+    rc = lib.af_find_first_token(ids.data_ptr(), R, L, int(token), out.data_ptr(), _stream())
+    _lib.check(rc, "af_find_first_token")
+    return out
+
+
+def splice_rows(dst: torch.Tensor, src: torch.Tensor, start: torch.Tensor, src_index: Optional[torch.Tensor] = None
+                ) -> torch.Tensor:
+    """dst fp32 [R, L, D]; src fp32 [S, K, D]; start int32 [R] (-1: untouched); src_index int32 [R] or None."""
+    lib = _lib.load()
+    _chk(dst, torch.float32, "dst")
+    _chk(src, torch.float32, "src")
+    _chk(start, torch.int32, "start")
+    if src_index is not None:
+        _chk(src_index, torch.int32, "src_index")
+    R, L, D = (int(v) for v in dst.shape)
+    rc = lib.af_splice_rows(dst.data_ptr(), src.data_ptr(), start.data_ptr(), _p(src_index), R, L, int(src.shape[1]), D,
+                            _stream())
+    _lib.check(rc, "af_splice_rows")
+    return dst
+
+
+def weighted_sum(a: torch.Tensor, b: torch.Tensor, c: Optional[torch.Tensor], w, out: Optional[torch.Tensor] = None
+                 ) -> torch.Tensor:
+    """out = w[0]*a + w[1]*b (+ w[2]*c), fp32."""
+    lib = _lib.load()
+    for t in (a, b) + ((c,) if c is not None else ()):
+        _chk(t, torch.float32, "operand")
+    if out is None:
+        out = torch.empty_like(a)
+    rc = lib.af_weighted_sum(a.data_ptr(), b.data_ptr(), _p(c), float(w[0]), float(w[1]), float(w[2]) if c is not None else 0.0,
+                             out.data_ptr(), a.numel(), _stream())
+    _lib.check(rc, "af_weighted_sum")
+    return out

@@ -52,6 +52,8 @@ typedef struct af_epilogue {
   int out_dtype;          /* AF_DTYPE_F32 | AF_DTYPE_BF16 */
   int geglu;              /* 1: GEGLU (attention.py:32-39): weight rows packed per 256-col tile as [128 value | 128 gate];
                              out[:, j] = (x.Wv_j + bv_j) * gelu(x.Wg_j + bg_j), N/2 bf16 output columns */
+  int act;                /* 0 none; 1 quick_gelu x*sigmoid(1.702x) applied to (acc + bias) before the residual add
+                             (CLIP text MLP, transformers QuickGELUActivation driven from arc2face_models.py:220) */
   float* gn_stats;        /* NULL, or [slots][N][2] fp32: per-channel (sum, sum of squares) of the values written, one
                              slot per 32 consecutive output rows (GEMM: slot = row / 32, rows-per-sample must be a
                              multiple of 32; conv: af_conv3x3_gn_slots() slots per sample).  Feeds af_groupnorm_finalize
@@ -106,6 +108,9 @@ int af_groupnorm_silu(const float* x0, int C0, const float* x1, int C1, int B, i
 /* nn.LayerNorm(C) (attention.py:267-269) on fp32 rows -> bf16. */
 int af_layernorm(const float* x, long long rows, int C, const float* gamma, const float* beta, float eps, void* y_bf16,
                  af_stream_t stream);
+/* same, fp32 output (CLIP final_layer_norm: arc2face_models.py:248, modules.py:370). */
+int af_layernorm_f32(const float* x, long long rows, int C, const float* gamma, const float* beta, float eps, float* y,
+                     af_stream_t stream);
 
 /* First / last convolutions of the UNet (4 latent channels), fp32 CUDA-core kernels that also convert
  * between the public NCHW layout and the internal NHWC one (openaimodel.py:527-533, :693-697). */
