@@ -229,3 +229,26 @@ def test_get_learned_conditioning_end_to_end(gold, models):
     err2 = _rel(c32[:32], c_ref)
     print(f"batch-32 conditioning rel-L2 vs oracle {err2:.3e}")
     assert err2 < TOL
+
+
+def test_adaface_wrapper_generates_and_installs_subject_embeddings(gold, models):
+    """AdaFaceWrapper surface (adaface_wrapper.py:207-254): id embedding -> 22-token Arc2Face pass -> SubjBasisGenerator
+    with num_out_layers=1 -> [16, 768] -> rows z_0..z_15 of the text encoder's embedding table."""
+    from adaprompt_b200.adaface_wrapper import AdaFaceWrapper
+    from adaprompt_b200.clip_text import CLIPTextModelWrapper
+    from oracle import text_oracle as to
+    te = CLIPTextModelWrapper()
+    te.load_state_dict(models["frozen"][1])
+    w = AdaFaceWrapper(None, "unused", "unused", "cuda", text_encoder=te, tokenizer=StubTokenizer(),
+                       subj_basis_generator=_sbg(models), arc2face_text_encoder=models["arc2face"][0])
+    assert w.placeholder_token_ids == list(range(49408, 49424))
+    face = gold["arc2face_forward"]["face_embs"][:1].cuda()
+    embs = w.generate_adaface_embeddings(None, pre_face_embs=face)
+    assert embs.shape == (16, 768)
+    table = w.text_encoder.text_model.embeddings.token_embedding.weight
+    assert torch.equal(table[49408:49424], embs)
+    # oracle: 22-token Arc2Face pass + SBG
+    sds = {k: models[k][1] for k in ("arc2face", "sbg")}
+    _, core = to.arc2face_forward_face_embs(sds["arc2face"], face.cpu(), 22)
+    subj, _ = to.subj_basis_generator_forward(sds["sbg"], core, torch.tensor([[1.0], [2.0], [4.0]]), num_out_layers=1)
+    assert _rel(embs, subj[0, 0]) < TOL

@@ -157,3 +157,39 @@ def test_no_cpu_fallback():
     rb = ResBlock(320, 1280, 0.0, out_channels=320)
     with pytest.raises(RuntimeError):
         rb(torch.randn(1, 320, 8, 8), torch.randn(1, 1280))
+
+
+def test_adaface_wrapper_forward_samples_latents(unet):
+    """AdaFaceWrapper.forward surface (adaface_wrapper.py:274-296) on the B200 components: scalar guidance scale, one
+    prompt embedding shared by the 16 cross-attention layers; returns latents (VAE decode is row N1)."""
+    import types
+    from adaprompt_b200.adaface_wrapper import AdaFaceWrapper
+    from adaprompt_b200.clip_text import CLIPTextConfigLite, CLIPTextModelWrapper
+    from adaprompt_b200.subj_basis_generator import SubjBasisGenerator
+
+    class Tok:
+        pad_token_id = 49407
+
+        def encode(self, text, add_special_tokens=False):
+            return [1014]
+
+        def __call__(self, text, max_length=77, **kw):
+            texts = [text] if isinstance(text, str) else list(text)
+            rows = []
+            for t in texts:
+                ids = [49406] + [49408 + int(w[2:]) if w.startswith("z_") else 1000 + (hash(w) % 4000) for w in t.split()][:max_length - 2] + [49407]
+                rows.append(ids + [49407] * (max_length - len(ids)))
+            return types.SimpleNamespace(input_ids=torch.tensor(rows))
+
+    cfg = CLIPTextConfigLite(num_hidden_layers=2)
+    torch.manual_seed(0)
+    sbg = SubjBasisGenerator(num_out_embs_per_layer=16, clip_tokenizer=Tok(), clip_config=cfg)
+    w = AdaFaceWrapper("text2img", "unused", "unused", "cuda", num_inference_steps=3, unet=unet,
+                       text_encoder=CLIPTextModelWrapper(cfg), tokenizer=Tok(), subj_basis_generator=sbg,
+                       arc2face_text_encoder=CLIPTextModelWrapper(cfg))
+    w.generate_adaface_embeddings(None, gen_rand_face=True)
+    noise = torch.randn(2, 4, 32, 32, generator=torch.Generator().manual_seed(1))
+    lat = w(noise, "a photo of z in a park", guidance_scale=4.0, out_image_count=2)
+    assert lat.shape == (2, 4, 32, 32) and torch.isfinite(lat).all()
+    lat1 = w(noise, "a photo of z in a park", guidance_scale=1.0, out_image_count=2)   # g == 1: uncond branch skipped
+    assert torch.isfinite(lat1).all() and not torch.equal(lat, lat1)
