@@ -9,15 +9,21 @@
 //   warps 4-7   softmax warpgroup of tile 0      warps 8-11  softmax warpgroup of tile 1
 //
 // While one warpgroup exponentiates its S tile the tensor core works for the other one, every SM sub-partition
-// holds two softmax warps (latency hiding), and K / V are fetched once per 256 queries.  tcgen05 executes a
-// thread's MMAs in issue order, so "S_{j+1} complete" implies "PV_j complete": the P buffer and the O
-// accumulator of a tile are free exactly when its next S arrives and no extra barrier is needed.
+// holds two softmax warps (latency hiding), and K / V are fetched once per 256 queries.
+// A softmax warpgroup copies its S tile to registers first and immediately hands the TMEM buffer back (s_free), so
+// the MMA warp computes S_{j+1} of the tile while the warpgroup is still exponentiating block j: the next scores
+// are already waiting when P_j has been written (profiles/r01_attention_pair_before.md: 43 % of the softmax warps'
+// time used to be spent waiting for S).  P / O reuse is ordered by pv_done (committed after PV_j).
 // The running max is only refreshed when it grows by more than 2^8 (lazy rescale): P stays <= 256 in bf16
 // and the O / l correction pass almost never runs after the first block.
 #include <math.h>
 
 #include "../../include/adaface_b200.h"
 #include "common.cuh"
+
+#ifndef AF_ATTN_STAGGER_CYCLES
+#define AF_ATTN_STAGGER_CYCLES 1100
+#endif
 
 namespace af {
 
@@ -102,10 +108,11 @@ __global__ void __launch_bounds__(384, 1) attention_pair_kernel(const __grid_con
   uint64_t* k_empty = k_full + C::KSTAGES;
   uint64_t* v_full = k_empty + C::KSTAGES;     // VSTAGES
   uint64_t* v_empty = v_full + C::VSTAGES;
-  uint64_t* s_full = v_empty + C::VSTAGES;     // 2 (per tile)
-  uint64_t* p_full = s_full + 2;               // 2 (per tile)
-  uint64_t* o_full = p_full + 2;               // 2 (per tile)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_full = v_empty + C::VSTAGES;     // 2 (per tile): S_j in TMEM
+  uint64_t* p_full = s_full + 2;               // 2 (per tile): P_j in shared memory
+  uint64_t* pv_done = p_full + 2;              // 2 (per tile): PV_j complete (P buffer / O accumulator reusable)
+  uint64_t* s_free = pv_done + 2;              // 2 (per tile): S_j copied to registers (TMEM buffer reusable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -130,7 +137,8 @@ __global__ void __launch_bounds__(384, 1) attention_pair_kernel(const __grid_con
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
       mbar_init(&p_full[t], 4);
-      mbar_init(&o_full[t], 1);
+      mbar_init(&pv_done[t], 1);
+      mbar_init(&s_free[t], 4);
     }
     mbar_fence_init();
   }
@@ -202,34 +210,59 @@ __global__ void __launch_bounds__(384, 1) attention_pair_kernel(const __grid_con
       issue_s(0, 0);
       issue_s(1, 0);
       tc_commit(&k_empty[0]);
-      ks = 1 % C::KSTAGES;
-      kph = (C::KSTAGES == 1) ? 1 : 0;
-      for (int j = 0; j < n_blocks; ++j) {
-        const bool more = j + 1 < n_blocks;
-        mbar_wait(&v_full[vs], vph);
-        if (more) mbar_wait(&k_full[ks], kph);
-        const uint32_t v_addr = smem_u32(smem + S::kVOff + vs * S::kVBytes);
+      // Event-driven issue: the two query tiles advance independently (an in-order schedule couples them - a
+      // warpgroup would wait for the other tile's softmax before its own PV is issued).  Per tile: S_b needs
+      // s_free (S_{b-1} copied to registers) and K_b; PV_b needs p_full (P_b written) and V_b.  A K / V ring slot
+      // is released when both tiles have consumed it.
+      int s_next[2] = {1, 1}, pv_next[2] = {0, 0};
+      uint64_t t_start;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+      uint32_t spins = 0;
+      while (pv_next[0] < n_blocks || pv_next[1] < n_blocks) {
+        bool progress = false;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_full[t], pph);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < BN / 16; ++k) {
-            const uint64_t ad = umma_desc_sw128(p_addr + t * S::kPBytes + (k >> 2) * 128 * 128) + 2 * (k & 3);
-            const uint64_t bd = umma_desc_sw128(v_addr + (k >> 2) * S::kVAtomBytes) + 2 * (k & 3);
-            tc_mma_ss(tmem_base + kTmemO[t], ad, bd, idesc_o, (j | k) != 0 ? 1u : 0u);
+          const int sb = s_next[t];
+          if (sb < n_blocks) {
+            const int slot = sb % C::KSTAGES;
+            if (mbar_test(&s_free[t], (sb - 1) & 1) && mbar_test(&k_full[slot], (sb / C::KSTAGES) & 1)) {
+              tc_fence_after();
+              issue_s(t, slot);
+              if (s_next[1 - t] > sb) tc_commit(&k_empty[slot]);   // the other tile already used K_b
+              s_next[t] = sb + 1;
+              progress = true;
+            }
           }
-          if (more) issue_s(t, ks);
-          else tc_commit(&o_full[t]);
+          const int pb = pv_next[t];
+          if (pb < n_blocks) {
+            const int slot = pb % C::VSTAGES;
+            if (mbar_test(&p_full[t], pb & 1) && mbar_test(&v_full[slot], (pb / C::VSTAGES) & 1)) {
+              tc_fence_after();
+              const uint32_t v_addr = smem_u32(smem + S::kVOff + slot * S::kVBytes);
+#pragma unroll
+              for (int k = 0; k < BN / 16; ++k) {
+                const uint64_t ad = umma_desc_sw128(p_addr + t * S::kPBytes + (k >> 2) * 128 * 128) + 2 * (k & 3);
+                const uint64_t bd = umma_desc_sw128(v_addr + (k >> 2) * S::kVAtomBytes) + 2 * (k & 3);
+                tc_mma_ss(tmem_base + kTmemO[t], ad, bd, idesc_o, (pb | k) != 0 ? 1u : 0u);
+              }
+              tc_commit(&pv_done[t]);
+              if (pv_next[1 - t] > pb) tc_commit(&v_empty[slot]);  // the other tile already used V_b
+              pv_next[t] = pb + 1;
+              progress = true;
+            }
+          }
         }
-        pph ^= 1;
-        tc_commit(&v_empty[vs]);
-        if (++vs == C::VSTAGES) { vs = 0; vph ^= 1; }
-        if (more) {
-          tc_commit(&k_empty[ks]);
-          if (++ks == C::KSTAGES) { ks = 0; kph ^= 1; }
+        if (!progress && (++spins & 0xfffff) == 0) {                // watchdog (same policy as mbar_wait)
+          uint64_t t_now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+          if (t_now - t_start > AF_WATCHDOG_NS) {
+            printf("af watchdog: attention MMA issue loop stuck (block %d,%d,%d s %d/%d pv %d/%d)\n", blockIdx.x,
+                   blockIdx.y, blockIdx.z, s_next[0], s_next[1], pv_next[0], pv_next[1]);
+            __trap();
+          }
         }
       }
+      (void)ks; (void)vs; (void)kph; (void)vph; (void)pph;
     }
   }
   } else {
@@ -246,6 +279,14 @@ __global__ void __launch_bounds__(384, 1) attention_pair_kernel(const __grid_con
     const uint32_t s_addr = tmem_base + kTmemS[t] + lane_off;
     const uint32_t o_addr = tmem_base + kTmemO[t] + lane_off;
 
+    // The two warpgroups share the SFU (ex2) units of their SM sub-partitions.  Started together they run in phase
+    // - both exponentiating at half rate, then both idle in TMEM loads / maxima - so tile 1 is started half a
+    // block late: its load / max phases then fall into tile 0's exponentiation phase and vice versa.
+    if (t == 1 && n_blocks > 2) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < AF_ATTN_STAGGER_CYCLES) {
+      }
+    }
     float m_ref = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_blocks; ++j) {
       const int key0 = j * BN;
@@ -255,6 +296,9 @@ __global__ void __launch_bounds__(384, 1) attention_pair_kernel(const __grid_con
 #pragma unroll
       for (int c = 0; c < BN; c += 32) tmem_ld32q(s_addr + c, reinterpret_cast<uint32_t*>(sc) + c);
       tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[t]);     // the MMA warp may overwrite S with the next block's scores
       if (key0 + BN > p.Nk || mrow != nullptr) {  // warp-uniform: tail block / explicit key mask only
 #pragma unroll
         for (int e = 0; e < BN; ++e) {
@@ -280,7 +324,11 @@ __global__ void __launch_bounds__(384, 1) attention_pair_kernel(const __grid_con
         m_ref = mx;
       }
       const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
-      // S_j complete implies PV_{j-1} complete (in-order tensor pipe): O and the P buffer are ours now
+      // PV_{j-1} complete: O and the P buffer are ours now
+      if (j > 0) {
+        mbar_wait(&pv_done[t], (j - 1) & 1);
+        tc_fence_after();
+      }
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll 1
         for (int c = 0; c < DV; c += 16) {
@@ -318,7 +366,7 @@ __global__ void __launch_bounds__(384, 1) attention_pair_kernel(const __grid_con
       if (lane == 0) mbar_arrive(&p_full[t]);
     }
     // epilogue: O / l -> bf16
-    mbar_wait(&o_full[t], 0);
+    mbar_wait(&pv_done[t], (n_blocks - 1) & 1);
     tc_fence_after();
     const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
     __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * p.Nq + q_row) * p.ldo + h * p.d;

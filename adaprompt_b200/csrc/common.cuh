@@ -41,6 +41,9 @@ int num_sms();
 // for dims 1..rank-1 (dim 0 is contiguous).  Returns 0 or an error code (message recorded).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr);
+// General form: elem_bytes 2 (bf16) | 4 (fp32); swizzle_bytes 128 | 64 | 0.
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr);
 
 // ---------------------------------------------------------------------------------------------
 // device helpers
@@ -87,6 +90,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
       "}\n"
       : "=r"(ok)
       : "r"(addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking probe of a phase (event-driven issue loops)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }

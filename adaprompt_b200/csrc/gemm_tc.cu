@@ -14,8 +14,14 @@
 //     tensor maps (A0 then A1).
 //
 // Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..9 = epilogue (TMEM -> registers -> smem transpose -> fused bias / time-embedding / residual /
-// GEGLU -> coalesced HBM stores).
+// warps 2..9 = epilogue.  An epilogue warp owns 32 rows (its TMEM lane quarter) x 32 columns per work item:
+//   TMEM -> registers (row per lane) -> + bias / per-sample time-embedding row / activation
+//        -> + fp32 residual that a TMA load prefetched into the warp's shared-memory slot (2-3 items ahead)
+//        -> result written back INTO the slot in the TMA 128B/64B-swizzled layout
+//        -> GroupNorm partial statistics read column-wise from the slot
+//        -> one TMA store (cp.async.bulk.tensor, shared -> global) per item.
+// No per-lane global address arithmetic, no transposition pass, edge tiles clipped by TMA; the memory-level
+// parallelism of the residual stream lives in the TMA queue instead of registers.
 // smem ring of kStages {A 128x64, B BNx64} 128B-swizzled tiles; 2 TMEM accumulator stages so the
 // epilogue of tile i overlaps the mainloop of tile i+1.
 #include "../../include/adaface_b200.h"
@@ -27,6 +33,9 @@ struct GemmParams {
   CUtensorMap tmA0;
   CUtensorMap tmA1;
   CUtensorMap tmB;
+  CUtensorMap tmOut;   // 4-D {cols, w, h, n} (linear: {N, M, 1, 1}), box = 32 columns x one warp's 32 rows
+  CUtensorMap tmRes;   // same geometry over the fp32 residual (== tmOut when there is none)
+  int sbx, sby;        // conv: the 32-row sub-box of a warp is sbx x sby x (32 / sbx / sby) pixels
   int M, N;            // output rows / packed output columns
   int num_kb;          // K blocks (64 wide) in total
   int cpb;             // K blocks per tap (== num_kb for linear)
@@ -54,18 +63,38 @@ struct GemmParams {
 
 constexpr int kEpiWarps = 8;                    // 2 warps per TMEM lane quarter, each takes every other 32-col chunk
 constexpr int kGemmThreads = 64 + kEpiWarps * 32;
-constexpr int kStagingBytes = kEpiWarps * 4096;  // 32 rows x 128 B per epilogue warp
+constexpr int kSmemBudget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
 
-template <int BN>
+// SLOTS = per-warp ring of epilogue slots (32 rows x 128 B; 64 B rows for the bf16-only GEGLU output).  3 slots keep
+// two residual chunks in flight per warp (64 KB per SM) for the memory-bound small-K GEMMs; everything else uses 2.
+template <int BN, bool GEGLU, int SLOTS>
 struct GemmCfg {
   static constexpr int kABytes = 128 * 128;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BN <= 64 ? 8 : (BN <= 128 ? 6 : (BN <= 160 ? 5 : 4));
+  static constexpr int kSlotBytes = GEGLU ? 2048 : 4096;
+  static constexpr int kSlotRegion = kEpiWarps * SLOTS * kSlotBytes;
+  static constexpr int kMaxStages = (kSmemBudget - kSlotRegion) / kStageBytes;
+  static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kAccStride = BN <= 128 ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccStride;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kSlotRegion + 1024 /*align*/ + 512 /*barriers*/;
+  static_assert(kStages >= 3, "not enough shared memory for the operand ring");
 };
+
+// ---- TMA store / bulk-group helpers -----------------------------------------------------------------
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // GELU for the GEGLU epilogue: x * Phi(x) in its tanh form, 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))), one MUFU
 // op per element.  |tanh form - erf form| <= 4.8e-4 absolute (rel-L2 2e-4 for unit-variance gates), an order of
@@ -83,18 +112,19 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 // QuickGELU of the CLIP text MLP (transformers QuickGELUActivation): x * sigmoid(1.702 x)
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
-template <int BN, bool GEGLU>
+template <int BN, bool GEGLU, int SLOTS>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, GEGLU, SLOTS>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* staging = smem + kStages * Cfg::kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  uint8_t* slots = smem + kStages * Cfg::kStageBytes;                 // [kEpiWarps][SLOTS][kSlotBytes], 1 KB aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slots + Cfg::kSlotRegion);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;                                  // [kEpiWarps][SLOTS] residual slot filled
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps * SLOTS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -104,6 +134,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     tma_prefetch_desc(&p.tmA0);
     tma_prefetch_desc(&p.tmA1);
     tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmOut);
+    tma_prefetch_desc(&p.tmRes);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -112,6 +144,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], kEpiWarps);
     }
+    for (int s = 0; s < kEpiWarps * SLOTS; ++s) mbar_init(&res_bar[s], 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -206,36 +239,100 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    // TMEM is read row-per-thread (lane == row).  Global traffic is made coalesced by a transpose through a
-    // swizzled per-warp shared-memory slab.
     const int ew = warp - 2;
     const int q = warp & 3;          // TMEM lane quarter this warp may access (hardware: warp id % 4)
-    const int half = ew >> 2;        // which 32-column chunks of the tile this warp takes
-    uint8_t* stg = staging + ew * 4096;
+    const int half = ew >> 2;        // which 32-column chunks of the tile this warp takes: c = half*32 + 64*i
+    uint8_t* my_slots = slots + ew * SLOTS * Cfg::kSlotBytes;
+    uint64_t* my_res_bar = res_bar + ew * SLOTS;
+    constexpr int kOutCols = GEGLU ? BN / 2 : BN;                       // output columns per tile
+    const int nch = (kOutCols - half * 32 + 63) / 64;                   // work items of this warp per tile
+    const bool has_res = !GEGLU && p.residual != nullptr;
+
+    // (tile, chunk) of this warp's j-th work item -> TMA coordinates {col, c1, c2, c3} of its 32x32 box
+    auto item_coords = [&](int j, int& c0, int& c1, int& c2, int& c3) -> bool {
+      const int t = blockIdx.x + (j / nch) * gridDim.x;
+      if (t >= num_tiles) return false;
+      const int n_tile = t % p.n_tiles, m_tile = t / p.n_tiles;
+      c0 = n_tile * kOutCols + half * 32 + 64 * (j % nch);
+      if (p.amode == 0) {
+        c1 = m_tile * 128 + q * 32; c2 = 0; c3 = 0;
+      } else {
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tn = m_tile / (p.tiles_w * p.tiles_h);
+        const int r0 = q * 32;
+        c1 = tw * p.bw + r0 % p.bw;
+        c2 = th * p.bh + (r0 / p.bw) % p.bh;
+        c3 = tn * p.nb + r0 / (p.bw * p.bh);
+      }
+      return true;
+    };
+    auto issue_res_load = [&](int j) {   // lane 0 only
+      int c0, c1, c2, c3;
+      if (!item_coords(j, c0, c1, c2, c3)) return;
+      const int sl = j % SLOTS;
+      mbar_arrive_expect_tx(&my_res_bar[sl], 4096);
+      tma_load_4d(my_slots + sl * Cfg::kSlotBytes, &p.tmRes, &my_res_bar[sl], c0, c1, c2, c3);
+    };
+    // residual prefetch distance: SLOTS - 1 items (SLOTS == 1: the next load waits for this item's store to drain)
+    constexpr int kAhead = SLOTS > 1 ? SLOTS - 1 : 1;
+    if (has_res && lane == 0) {
+#pragma unroll
+      for (int j = 0; j < kAhead; ++j) issue_res_load(j);
+    }
+
+    int item = 0;                      // running work-item index of this warp (slot = item % SLOTS)
     int acc = 0;
     uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      // this lane's output row (for the per-sample rowbias and the statistics mask)
+      bool row_ok;
+      uint32_t grow;
+      long long stat_slot = -1;
+      if (p.amode == 0) {
+        grow = m_tile * 128 + q * 32 + lane;
+        row_ok = grow < static_cast<uint32_t>(p.M);
+        stat_slot = static_cast<long long>(m_tile) * 4 + q;
+      } else {
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tn = m_tile / (p.tiles_w * p.tiles_h);
+        const int r = q * 32 + lane;
+        const int n = tn * p.nb + r / (p.bw * p.bh), h = th * p.bh + (r / p.bw) % p.bh, w = tw * p.bw + r % p.bw;
+        row_ok = n < p.B && h < p.H && w < p.W;
+        grow = (n * p.H + h) * p.W + w;
+        const int per = p.bw * p.bh;                       // pixels of one sample inside the tile (>= 32 if stats)
+        const int n0s = tn * p.nb + (q * 32) / per;
+        if (n0s < p.B)
+          stat_slot = static_cast<long long>(n0s) * p.gn_slots + (th * p.tiles_w + tw) * (per >> 5) + (((q * 32) % per) >> 5);
+      }
+      const float* rb_row = nullptr;
+      if (!GEGLU && p.rowbias && row_ok) rb_row = p.rowbias + static_cast<long long>(grow / static_cast<uint32_t>(p.rows_per_group)) * p.ld_rowbias;
+      const uint32_t row_mask = __ballot_sync(0xffffffffu, row_ok);
 
-    if constexpr (GEGLU) {
-      // ---- GEGLU (attention.py:32-39): out[:, j] = (acc[:, j] + bv[j]) * gelu(acc[:, BN/2 + j] + bg[j]), bf16.
-      // The math runs in the TMEM layout (one row per lane, 32 consecutive columns); only the bf16 result is
-      // transposed (2 KB per chunk) so that every warp store instruction writes 8 rows x 64 contiguous bytes.
-      const int orow = lane >> 2;      // row within a group of 8 rows in the coalesced phase
-      const int ochk = lane & 3;       // 16-byte chunk within the 64-byte bf16 row
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
-        const long long row0 = static_cast<long long>(m_tile) * 128 + q * 32;
-        mbar_wait(&tfull_bar[acc], acc_phase);
-        tc_fence_after();
-        const uint32_t t_acc = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-        for (int c = half * 32; c < BN / 2; c += 64) {
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+
+      for (int i = 0; i < nch; ++i, ++item) {
+        const int c = half * 32 + 64 * i;                    // first accumulator column of the chunk
+        const int col0 = n_tile * kOutCols + c;              // first output column
+        const int sl = item % SLOTS;
+        uint8_t* slot = my_slots + sl * Cfg::kSlotBytes;
+        int c0, c1, c2, c3;
+        item_coords(item, c0, c1, c2, c3);
+
+        if constexpr (GEGLU) {
+          // out[:, j] = (acc[:, j] + bv[j]) * gelu(acc[:, BN/2 + j] + bg[j]) -> bf16, 64-byte rows, SWIZZLE_64B
           uint32_t v[32], g[32];
           tmem_ld32(t_acc + c, v);
           tmem_ld32(t_acc + BN / 2 + c, g);
-          const int pc = n_tile * BN + c;              // packed column of the value half (bias index)
-          const int col0 = n_tile * (BN / 2) + c;      // first output column of this chunk
-          const bool col_ok = col0 < p.N / 2;          // N/2 is a multiple of 128: chunks are all-or-nothing
+          const int pc = n_tile * BN + c;                    // packed column of the value half (bias index)
+          const bool col_ok = col0 < p.N / 2;                // N/2 is a multiple of 128: chunks are all-or-nothing
+          if (lane == 0) bulk_wait_read<SLOTS - 1>();        // the store that last used this slot has read it
+          __syncwarp();
           tmem_ld_wait();
           uint32_t pk[16];
 #pragma unroll
@@ -252,186 +349,98 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             pk[2 * j] = pack_bf16x2(o0, o1);
             pk[2 * j + 1] = pack_bf16x2(o2, o3);
           }
-          // slab: [32 rows][64 B], 16-byte chunks XOR-swizzled with (row >> 1) & 3 (conflict-free both ways)
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+            *reinterpret_cast<uint4*>(slot + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
                 make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          fence_async_smem();
           __syncwarp();
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int R = 8 * k + orow;
-            const uint4 o = *reinterpret_cast<const uint4*>(stg + R * 64 + ((ochk ^ ((R >> 1) & 3)) << 4));
-            const long long gr = row0 + R;
-            if (gr < p.M && col_ok)
-              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + gr * p.ldo + col0 + ochk * 8) = o;
+          if (lane == 0) {
+            tma_store_4d(&p.tmOut, slot, c0, c1, c2, c3);
+            bulk_commit();
           }
-          __syncwarp();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
-      }
-    } else {
-      // ---- generic: out = acc + bias[col] + rowbias[row / rows_per_group, col] + residual[row, col]  (fp32 | bf16)
-      // Each 32x32 fp32 chunk is transposed through a swizzled 4 KB slab: one warp instruction then covers
-      // 4 rows x 128 B (fp32).  The residual / rowbias operands of chunk c+1 are requested before chunk c is
-      // processed (and those of a tile's first chunk before its accumulator is complete), so the loads overlap
-      // the MMA wait, the TMEM read and the stores.
-      const int sub = lane >> 3;       // row within a group of 4 rows in the coalesced phase
-      const int cl = lane & 7;         // 16-byte column chunk within the 128-byte row
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
-        // rows this lane stores in the coalesced phase: tile row q*32 + 4k + sub, k = 0..7 (element offsets fit
-        // 32 bits: checked on the host)
-        uint32_t grow[8];              // output row index
-        uint32_t aoff[8];              // element offset of the row's auxiliary operand (residual, else rowbias)
-        uint32_t valid = 0;
-        long long stat_slot = -1;      // flat GroupNorm-statistics slot of this warp's 32 rows
-        if (p.amode == 0) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            grow[k] = m_tile * 128 + q * 32 + 4 * k + sub;
-            if (grow[k] < static_cast<uint32_t>(p.M)) valid |= 1u << k;
-          }
-          stat_slot = static_cast<long long>(m_tile) * 4 + q;
         } else {
-          const int tw = m_tile % p.tiles_w;
-          const int th = (m_tile / p.tiles_w) % p.tiles_h;
-          const int tn = m_tile / (p.tiles_w * p.tiles_h);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int r = q * 32 + 4 * k + sub;
-            const int rw = r % p.bw;
-            const int rh = (r / p.bw) % p.bh;
-            const int rn = r / (p.bw * p.bh);
-            const int n = tn * p.nb + rn, h = th * p.bh + rh, w = tw * p.bw + rw;
-            if (n < p.B && h < p.H && w < p.W) valid |= 1u << k;
-            grow[k] = (n * p.H + h) * p.W + w;
-          }
-          const int per = p.bw * p.bh;                       // pixels of one sample inside the tile (>= 32 if stats)
-          const int n0s = tn * p.nb + (q * 32) / per;
-          if (n0s < p.B)
-            stat_slot = static_cast<long long>(n0s) * p.gn_slots + (th * p.tiles_w + tw) * (per >> 5) + (((q * 32) % per) >> 5);
-        }
-        // ONE auxiliary fp32 operand is prefetched per row: the residual if present, else the per-sample rowbias.
-        // (Both together only occur in tests; the rowbias is then added at consumption time.)
-        const float* aux = p.residual ? p.residual : p.rowbias;
-        const bool late_rowbias = p.residual != nullptr && p.rowbias != nullptr;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (p.residual) aoff[k] = grow[k] * static_cast<uint32_t>(p.ldr);
-          else if (p.rowbias) aoff[k] = (grow[k] / static_cast<uint32_t>(p.rows_per_group)) * static_cast<uint32_t>(p.ld_rowbias);
-          else aoff[k] = 0;
-        }
-        const int ncols = p.N;
-        auto load_aux = [&](int c, float4 (&rs)[8]) {
-          const int col = n_tile * BN + c + 4 * cl;
-          const bool col_ok = col < ncols;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const bool ok = ((valid >> k) & 1u) && col_ok;
-            const float4* ptr = reinterpret_cast<const float4*>(aux + aoff[k] + (ok ? col : 0));
-            rs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) rs[k] = *ptr;
-          }
-        };
-        const bool has_aux = aux != nullptr;
-        float4 rs[8];
-        if (has_aux) load_aux(half * 32, rs);
-        else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) rs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-
-        mbar_wait(&tfull_bar[acc], acc_phase);
-        tc_fence_after();
-        const uint32_t t_acc = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-
-        constexpr int kChunkIters = (BN + 63) / 64;
-#pragma unroll
-        for (int it = 0; it < kChunkIters; ++it) {
-          const int c = half * 32 + it * 64;
-          if (c >= BN) break;
-          const int col = n_tile * BN + c + 4 * cl;  // this lane's 4 output columns
-          const bool col_ok = col < ncols;
           uint32_t v[32];
           tmem_ld32(t_acc + c, v);
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-          float4 rsn[8];
-          const bool more = c + 64 < BN;
-          if (has_aux && more) load_aux(c + 64, rsn);
+          const bool col_ok = col0 < p.N;
+          float4 b4[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias && col0 + 4 * j < p.N) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+            if (rb_row && col0 + 4 * j < p.N) {
+              const float4 rb = __ldg(reinterpret_cast<const float4*>(rb_row + col0) + j);
+              b4[j].x += rb.x; b4[j].y += rb.y; b4[j].z += rb.z; b4[j].w += rb.w;
+            }
+          }
+          if (has_res) {
+            mbar_wait(&my_res_bar[sl], (item / SLOTS) & 1);   // residual chunk landed in the slot
+          } else {
+            if (lane == 0) bulk_wait_read<SLOTS - 1>();      // the store that last used this slot has read it
+            __syncwarp();
+          }
           tmem_ld_wait();
+          float4 o[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          __syncwarp();
-          float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), q4 = s4;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int R = 4 * k + sub;
-            const float4 a = *reinterpret_cast<const float4*>(stg + R * 128 + ((cl ^ (R & 7)) << 4));
-            float4 t4 = make_float4(a.x + b4.x, a.y + b4.y, a.z + b4.z, a.w + b4.w);
+          for (int j = 0; j < 8; ++j) {
+            float4 t4 = make_float4(__uint_as_float(v[4 * j]) + b4[j].x, __uint_as_float(v[4 * j + 1]) + b4[j].y,
+                                    __uint_as_float(v[4 * j + 2]) + b4[j].z, __uint_as_float(v[4 * j + 3]) + b4[j].w);
             if (p.act == 1) {
               t4.x = quick_gelu(t4.x); t4.y = quick_gelu(t4.y); t4.z = quick_gelu(t4.z); t4.w = quick_gelu(t4.w);
             }
-            float4 o = make_float4(t4.x + rs[k].x, t4.y + rs[k].y, t4.z + rs[k].z, t4.w + rs[k].w);
-            if (((valid >> k) & 1u) && col_ok) {
-              if (late_rowbias) {
-                const float4 rb = __ldg(reinterpret_cast<const float4*>(
-                    p.rowbias + static_cast<long long>(grow[k] / static_cast<uint32_t>(p.rows_per_group)) * p.ld_rowbias + col));
-                o.x += rb.x; o.y += rb.y; o.z += rb.z; o.w += rb.w;
-              }
-              if (p.out_bf16) {
-                uint2 pk;
-                pk.x = pack_bf16x2(o.x, o.y);
-                pk.y = pack_bf16x2(o.z, o.w);
-                *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + grow[k] * static_cast<uint32_t>(p.ldo) + col) = pk;
-              } else {
-                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + grow[k] * static_cast<uint32_t>(p.ldo) + col) = o;
-              }
-              s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
-              q4.x = fmaf(o.x, o.x, q4.x); q4.y = fmaf(o.y, o.y, q4.y);
-              q4.z = fmaf(o.z, o.z, q4.z); q4.w = fmaf(o.w, o.w, q4.w);
+            if (has_res) {
+              const float4 r4 = *reinterpret_cast<const float4*>(slot + lane * 128 + ((j ^ (lane & 7)) << 4));
+              t4.x += r4.x; t4.y += r4.y; t4.z += r4.z; t4.w += r4.w;
             }
+            o[j] = t4;
           }
-          if (p.gn_stats) {
-            // fixed-order reduction over the 4 row sub-groups (deterministic), lanes 0..7 publish 4 channels each
+          if (p.out_bf16) {
+            if (has_res) __syncwarp();                       // every lane has read its residual row
 #pragma unroll
-            for (int o = 8; o <= 16; o <<= 1) {
-              s4.x += __shfl_xor_sync(0xffffffffu, s4.x, o); s4.y += __shfl_xor_sync(0xffffffffu, s4.y, o);
-              s4.z += __shfl_xor_sync(0xffffffffu, s4.z, o); s4.w += __shfl_xor_sync(0xffffffffu, s4.w, o);
-              q4.x += __shfl_xor_sync(0xffffffffu, q4.x, o); q4.y += __shfl_xor_sync(0xffffffffu, q4.y, o);
-              q4.z += __shfl_xor_sync(0xffffffffu, q4.z, o); q4.w += __shfl_xor_sync(0xffffffffu, q4.w, o);
-            }
-            if (sub == 0 && col_ok && stat_slot >= 0) {
-              float4* dst = reinterpret_cast<float4*>(p.gn_stats + (stat_slot * ncols + col) * 2);
-              dst[0] = make_float4(s4.x, q4.x, s4.y, q4.y);
-              dst[1] = make_float4(s4.z, q4.z, s4.w, q4.w);
-            }
-          }
-          if (has_aux && more) {
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(slot + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(pack_bf16x2(o[2 * j].x, o[2 * j].y), pack_bf16x2(o[2 * j].z, o[2 * j].w),
+                             pack_bf16x2(o[2 * j + 1].x, o[2 * j + 1].y), pack_bf16x2(o[2 * j + 1].z, o[2 * j + 1].w));
+          } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) rs[k] = rsn[k];   // fully unrolled chunk loop: pure register renaming
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(slot + lane * 128 + ((j ^ (lane & 7)) << 4)) = o[j];
           }
+          fence_async_smem();
           __syncwarp();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+          if (p.gn_stats && !p.out_bf16) {
+            // per-channel (sum, sum of squares) over this warp's valid rows: lane = column, fixed row order
+            float s = 0.f, ss = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              if ((row_mask >> r) & 1u) {
+                const float x = *reinterpret_cast<const float*>(slot + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
+                s += x;
+                ss = fmaf(x, x, ss);
+              }
+            }
+            if (stat_slot >= 0 && col0 + lane < p.N)
+              *reinterpret_cast<float2*>(p.gn_stats + (stat_slot * p.N + col0 + lane) * 2) = make_float2(s, ss);
+          }
+          if (lane == 0) {
+            if (col_ok) tma_store_4d(&p.tmOut, slot, c0, c1, c2, c3);
+            bulk_commit();
+            if (has_res) {
+              bulk_wait_read<(SLOTS > 1 ? 1 : 0)>();         // the previous item's store has drained its slot ...
+              issue_res_load(item + kAhead);                 // ... which is the slot of item + kAhead
+            }
+          }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
     }
+    if (lane == 0) bulk_wait_all();      // shared memory must outlive the bulk stores
   }
 
   tc_fence_before();
@@ -445,30 +454,65 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool GEGLU>
+template <int BN, bool GEGLU, int SLOTS>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, GEGLU, SLOTS>;
   static bool configured = false;
   if (!configured) {
-    AF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    AF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, GEGLU, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BN, GEGLU><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
+  gemm_tc_kernel<BN, GEGLU, SLOTS><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
   AF_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
 
 static int dispatch_gemm(int bn, const GemmParams& p, cudaStream_t stream) {
-  if (p.geglu) return launch_gemm<256, true>(p, stream);
+  if (p.geglu) return launch_gemm<256, true, 2>(p, stream);
+  // epilogue slots per warp: 3 (two residual chunks in flight) for the memory-bound linear GEMMs with a residual,
+  // 1 for the K-deep convolutions (their epilogue has slack; the shared memory goes to the operand ring), else 2
+  const int slots = p.amode != 0 ? 1 : (p.residual != nullptr ? 3 : 2);
   switch (bn) {
-    case 64: return launch_gemm<64, false>(p, stream);
-    case 128: return launch_gemm<128, false>(p, stream);
-    case 160: return launch_gemm<160, false>(p, stream);
-    case 256: return launch_gemm<256, false>(p, stream);
+    case 64: return slots == 1 ? launch_gemm<64, false, 1>(p, stream) : slots == 3 ? launch_gemm<64, false, 3>(p, stream) : launch_gemm<64, false, 2>(p, stream);
+    case 128: return slots == 1 ? launch_gemm<128, false, 1>(p, stream) : slots == 3 ? launch_gemm<128, false, 3>(p, stream) : launch_gemm<128, false, 2>(p, stream);
+    case 160: return slots == 1 ? launch_gemm<160, false, 1>(p, stream) : slots == 3 ? launch_gemm<160, false, 3>(p, stream) : launch_gemm<160, false, 2>(p, stream);
+    case 256: return launch_gemm<256, false, 1>(p, stream);
     default: set_error("unsupported BN %d (64/128/160/256)", bn); return -1;
   }
+}
+
+// Output / residual tensor maps: 4-D {cols, w, h, n} with one warp's 32 rows x 32 columns as the box.
+static int make_epilogue_maps(GemmParams& p, int out_cols, bool conv) {
+  const int oes = p.out_bf16 ? 2 : 4;
+  uint64_t dims[4], ostr[3], rstr[3];
+  uint32_t box[4];
+  dims[0] = static_cast<uint64_t>(out_cols);
+  if (!conv) {
+    dims[1] = static_cast<uint64_t>(p.M); dims[2] = 1; dims[3] = 1;
+    box[0] = 32; box[1] = 32; box[2] = 1; box[3] = 1;
+    p.sbx = 32; p.sby = 1;
+    ostr[0] = p.ldo * oes; ostr[1] = ostr[0] * dims[1]; ostr[2] = ostr[1];
+    rstr[0] = p.ldr * 4; rstr[1] = rstr[0] * dims[1]; rstr[2] = rstr[1];
+  } else {
+    dims[1] = p.W; dims[2] = p.H; dims[3] = p.B;
+    int sbx = p.bw < 32 ? p.bw : 32;
+    int sby = p.bh < 32 / sbx ? p.bh : 32 / sbx;
+    int sbz = 32 / (sbx * sby);
+    p.sbx = sbx; p.sby = sby;
+    box[0] = 32; box[1] = sbx; box[2] = sby; box[3] = sbz;
+    ostr[0] = p.ldo * oes; ostr[1] = ostr[0] * p.W; ostr[2] = ostr[1] * p.H;
+    rstr[0] = p.ldr * 4; rstr[1] = rstr[0] * p.W; rstr[2] = rstr[1] * p.H;
+  }
+  int rc = make_tmap(&p.tmOut, p.out, oes, p.out_bf16 ? 64 : 128, 4, dims, ostr, box);
+  if (rc) return rc;
+  p.tmRes = p.tmOut;
+  if (p.residual) {
+    AF_CHECK_ARG((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0, "epilogue: residual not 16B aligned");
+    rc = make_tmap(&p.tmRes, p.residual, 4, 128, 4, dims, rstr, box);
+  }
+  return rc;
 }
 
 static int pick_bn(int N, int geglu, int bn_hint) {
@@ -564,6 +608,8 @@ extern "C" int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* 
   p.n_tiles = (N + bn - 1) / bn;
   int rc = fill_epilogue(p, ep, ep->geglu ? N / 2 : N);
   if (rc) return rc;
+  rc = make_epilogue_maps(p, ep->geglu ? N / 2 : N, false);
+  if (rc) return rc;
   return dispatch_gemm(bn, p, stream);
 }
 
@@ -655,5 +701,7 @@ extern "C" int af_conv3x3_bf16(const void* X0, int C0, const void* X1, int C1, c
     p.gn_slots = af_conv3x3_gn_slots(Ho, Wo);
     AF_CHECK_ARG(p.gn_slots > 0, "af_conv3x3_bf16: gn_stats unsupported for %dx%d outputs (fewer than 32 pixels per tile row group)", Ho, Wo);
   }
+  rc = make_epilogue_maps(p, Cout, true);
+  if (rc) return rc;
   return dispatch_gemm(bn, p, stream);
 }

@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "conv3x3 or gemm" --timeout 300 -p no:cacheprovider 2>&1 | tail -2
-python scripts/bench_gemm.py all > gpurun_out/gemm_bench.log 2>&1; grep conv gpurun_out/gemm_bench.log
 python scripts/attn_one.py > gpurun_out/plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:attention_pair -s 2 -c 1 -o gpurun_out/attn_prof -f python scripts/attn_one.py > gpurun_out/ncu.log 2>&1
 echo "ncu rc $?"; cat gpurun_out/plain.log; tail -2 gpurun_out/ncu.log

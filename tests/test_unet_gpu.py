@@ -184,7 +184,7 @@ def test_adaface_wrapper_forward_samples_latents(unet):
     cfg = CLIPTextConfigLite(num_hidden_layers=2)
     torch.manual_seed(0)
     sbg = SubjBasisGenerator(num_out_embs_per_layer=16, clip_tokenizer=Tok(), clip_config=cfg)
-    w = AdaFaceWrapper("text2img", "unused", "unused", "cuda", num_inference_steps=3, unet=unet,
+    w = AdaFaceWrapper("text2img", "unused", "unused", "cuda", num_inference_steps=5, unet=unet,
                        text_encoder=CLIPTextModelWrapper(cfg), tokenizer=Tok(), subj_basis_generator=sbg,
                        arc2face_text_encoder=CLIPTextModelWrapper(cfg))
     w.generate_adaface_embeddings(None, gen_rand_face=True)
