@@ -67,10 +67,11 @@ constexpr int kSmemBudget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
 
 // SLOTS = per-warp ring of epilogue slots (32 rows x 128 B; 64 B rows for the bf16-only GEGLU output).  3 slots keep
 // two residual chunks in flight per warp (64 KB per SM) for the memory-bound small-K GEMMs; everything else uses 2.
-template <int BN, bool GEGLU, int SLOTS>
+template <int BN, bool GEGLU, int SLOTS, bool CTA2>
 struct GemmCfg {
   static constexpr int kABytes = 128 * 128;
-  static constexpr int kBBytes = BN * 128;
+  static constexpr int kBRows = CTA2 ? BN / 2 : BN;      // CTA pair: each CTA stages half of the B tile
+  static constexpr int kBBytes = kBRows * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSlotBytes = GEGLU ? 2048 : 4096;
   static constexpr int kSlotRegion = kEpiWarps * SLOTS * kSlotBytes;
@@ -79,6 +80,7 @@ struct GemmCfg {
   static constexpr int kAccStride = BN <= 128 ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccStride;
   static constexpr int kSmemBytes = kStages * kStageBytes + kSlotRegion + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int kTxBytes = CTA2 ? 2 * kStageBytes : kStageBytes;   // bytes landing per stage (both CTAs)
   static_assert(kStages >= 3, "not enough shared memory for the operand ring");
 };
 
@@ -112,9 +114,9 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 // QuickGELU of the CLIP text MLP (transformers QuickGELUActivation): x * sigmoid(1.702 x)
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
-template <int BN, bool GEGLU, int SLOTS>
+template <int BN, bool GEGLU, int SLOTS, bool CTA2>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN, GEGLU, SLOTS>;
+  using Cfg = GemmCfg<BN, GEGLU, SLOTS, CTA2>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -128,7 +130,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  // CTA pair: both CTAs walk the same sequence of 256-row pair tiles; rank r owns m_tile = 2 * pair_m + r
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int tile_first = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int num_tiles = (CTA2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
+  auto tile_mn = [&](int t, int& n_tile, int& m_tile) {
+    n_tile = t % p.n_tiles;
+    const int pm = t / p.n_tiles;
+    m_tile = CTA2 ? 2 * pm + static_cast<int>(cta_rank) : pm;
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmA0);
@@ -142,17 +154,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kEpiWarps);
+      mbar_init(&tempty_bar[s], CTA2 ? 2 * kEpiWarps : kEpiWarps);   // pair: the leader's barrier collects both CTAs
     }
     for (int s = 0; s < kEpiWarps * SLOTS; ++s) mbar_init(&res_bar[s], 1);
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CTA2) {
+      tmem_alloc2(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -161,10 +178,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
-        const int n0 = n_tile * BN;
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+        int n_tile, m_tile;
+        tile_mn(tile, n_tile, m_tile);
+        const int n0 = n_tile * BN + (CTA2 ? static_cast<int>(cta_rank) * (BN / 2) : 0);
         int cw = 0, ch = 0, cn = 0;
         if (p.amode != 0) {
           cw = (m_tile % p.tiles_w) * p.bw;
@@ -175,25 +192,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kTxBytes);
           const int tap = kb / p.cpb;
           const int cblk = kb - tap * p.cpb;
           const bool second = cblk >= p.kb_split;
           const CUtensorMap* tmA = second ? &p.tmA1 : &p.tmA0;
           const int kc = (second ? cblk - p.kb_split : cblk) * 64;
-          if (p.amode == 0) {
-            tma_load_2d(sa, tmA, &full_bar[stage], kc, m_tile * 128);
-          } else if (p.amode == 1) {
-            const int ky = tap / 3, kx = tap - ky * 3;
-            tma_load_4d(sa, tmA, &full_bar[stage], kc, cw + kx - 1, ch + ky - 1, cn);
+          const int ky = tap / 3, kx = tap - ky * 3;
+          // stride 2: input row 2*oh + ky - 1  ->  (coarse row oh + dh, parity ph)
+          const int ph = (ky == 1) ? 0 : 1, dh = (ky == 0) ? -1 : 0;
+          const int pw = (kx == 1) ? 0 : 1, dw = (kx == 0) ? -1 : 0;
+          if constexpr (CTA2) {
+            if (p.amode == 0) tma_load_2d_pair(sa, tmA, &full_bar[stage], kc, m_tile * 128);
+            else if (p.amode == 1) tma_load_4d_pair(sa, tmA, &full_bar[stage], kc, cw + kx - 1, ch + ky - 1, cn);
+            else tma_load_5d_pair(sa, tmA, &full_bar[stage], pw * p.C0 + kc, cw + dw, ph, ch + dh, cn);
+            tma_load_2d_pair(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
           } else {
-            const int ky = tap / 3, kx = tap - ky * 3;
-            // input row 2*oh + ky - 1  ->  (coarse row oh + dh, parity ph)
-            const int ph = (ky == 1) ? 0 : 1, dh = (ky == 0) ? -1 : 0;
-            const int pw = (kx == 1) ? 0 : 1, dw = (kx == 0) ? -1 : 0;
-            tma_load_5d(sa, tmA, &full_bar[stage], pw * p.C0 + kc, cw + dw, ph, ch + dh, cn);
+            if (p.amode == 0) tma_load_2d(sa, tmA, &full_bar[stage], kc, m_tile * 128);
+            else if (p.amode == 1) tma_load_4d(sa, tmA, &full_bar[stage], kc, cw + kx - 1, ch + ky - 1, cn);
+            else tma_load_5d(sa, tmA, &full_bar[stage], pw * p.C0 + kc, cw + dw, ph, ch + dh, cn);
+            tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
           }
-          tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -202,14 +221,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    // ------------------------------------------------------------------ MMA issuer (pair: leader CTA only)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 256 : 128, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
@@ -222,15 +241,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // +32 bytes (16 bf16) along K inside the 128B swizzle atom == +2 in the >>4 address field
-            tc_mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (CTA2) tc_mma_ss2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else tc_mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);
+          if constexpr (CTA2) tc_commit2(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(&tfull_bar[acc]);
+        if constexpr (CTA2) tc_commit2(&tfull_bar[acc]); else tc_commit(&tfull_bar[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -250,9 +270,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 
     // (tile, chunk) of this warp's j-th work item -> TMA coordinates {col, c1, c2, c3} of its 32x32 box
     auto item_coords = [&](int j, int& c0, int& c1, int& c2, int& c3) -> bool {
-      const int t = blockIdx.x + (j / nch) * gridDim.x;
+      const int t = tile_first + (j / nch) * tile_step;
       if (t >= num_tiles) return false;
-      const int n_tile = t % p.n_tiles, m_tile = t / p.n_tiles;
+      int n_tile, m_tile;
+      tile_mn(t, n_tile, m_tile);
       c0 = n_tile * kOutCols + half * 32 + 64 * (j % nch);
       if (p.amode == 0) {
         c1 = m_tile * 128 + q * 32; c2 = 0; c3 = 0;
@@ -284,9 +305,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     int item = 0;                      // running work-item index of this warp (slot = item % SLOTS)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+      int n_tile, m_tile;
+      tile_mn(tile, n_tile, m_tile);
       // this lane's output row (for the per-sample rowbias and the statistics mask)
       bool row_ok;
       uint32_t grow;
@@ -294,7 +315,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       if (p.amode == 0) {
         grow = m_tile * 128 + q * 32 + lane;
         row_ok = grow < static_cast<uint32_t>(p.M);
-        stat_slot = static_cast<long long>(m_tile) * 4 + q;
+        if (m_tile < p.m_tiles) stat_slot = static_cast<long long>(m_tile) * 4 + q;   // (pair: odd tile count)
       } else {
         const int tw = m_tile % p.tiles_w;
         const int th = (m_tile / p.tiles_w) % p.tiles_h;
@@ -434,7 +455,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (CTA2 && !leader) mbar_arrive_cta(&tempty_bar[acc], 0);   // the leader's MMA warp owns both accumulators
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -444,41 +468,77 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all(); else __syncthreads();   // pair: no CTA may leave while its peer can still signal it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (CTA2) tmem_dealloc2(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool GEGLU, int SLOTS>
+static int g_pair_mode = 1;   // 1: CTA pairs (cta_group::2) whenever a GEMM has at least two 128-row tiles; 0: never
+
+template <int BN, bool GEGLU, int SLOTS, bool CTA2>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, GEGLU, SLOTS>;
+  using Cfg = GemmCfg<BN, GEGLU, SLOTS, CTA2>;
   static bool configured = false;
   if (!configured) {
-    AF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, GEGLU, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    AF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, GEGLU, SLOTS, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::kSmemBytes));
     configured = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BN, GEGLU, SLOTS><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
+  if constexpr (CTA2) {
+    const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int max_pairs = num_sms() / 2;
+    const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    AF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, GEGLU, SLOTS, CTA2>, p));
+  } else {
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    gemm_tc_kernel<BN, GEGLU, SLOTS, CTA2><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
+  }
   AF_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
 
-static int dispatch_gemm(int bn, const GemmParams& p, cudaStream_t stream) {
-  if (p.geglu) return launch_gemm<256, true, 2>(p, stream);
+// Measured on B200 (profiles/r01_pair_vs_single.md): the pair schedule wins for linear GEMMs with N tiles >= 160 and
+// at least two waves of pair tiles (+7 % on the FF2 shapes, +17 % on 8192^3 with 256-wide tiles) and loses ~3 % on the
+// implicit-GEMM convolutions, so mode 1 ("auto") uses it only there; mode 2 forces it wherever it is legal (tests).
+static bool want_pair(int m_tiles, int n_tiles, int bn, int amode) {
+  if (g_pair_mode == 0 || m_tiles < 2) return false;
+  if (g_pair_mode == 2) return true;
+  return amode == 0 && bn >= 160 && ((m_tiles + 1) / 2) * n_tiles >= num_sms();
+}
+
+template <int BN, bool GEGLU, int SLOTS>
+static int launch_gemm_mode(const GemmParams& p, bool pair, cudaStream_t stream) {
+  return pair ? launch_gemm<BN, GEGLU, SLOTS, true>(p, stream) : launch_gemm<BN, GEGLU, SLOTS, false>(p, stream);
+}
+
+static int dispatch_gemm(int bn, const GemmParams& p, bool pair, cudaStream_t stream) {
+  if (p.geglu) return launch_gemm_mode<256, true, 2>(p, pair, stream);
   // epilogue slots per warp: 3 (two residual chunks in flight) for the memory-bound linear GEMMs with a residual,
   // 1 for the K-deep convolutions (their epilogue has slack; the shared memory goes to the operand ring), else 2
   const int slots = p.amode != 0 ? 1 : (p.residual != nullptr ? 3 : 2);
   switch (bn) {
-    case 64: return slots == 1 ? launch_gemm<64, false, 1>(p, stream) : slots == 3 ? launch_gemm<64, false, 3>(p, stream) : launch_gemm<64, false, 2>(p, stream);
-    case 128: return slots == 1 ? launch_gemm<128, false, 1>(p, stream) : slots == 3 ? launch_gemm<128, false, 3>(p, stream) : launch_gemm<128, false, 2>(p, stream);
-    case 160: return slots == 1 ? launch_gemm<160, false, 1>(p, stream) : slots == 3 ? launch_gemm<160, false, 3>(p, stream) : launch_gemm<160, false, 2>(p, stream);
-    case 256: return launch_gemm<256, false, 1>(p, stream);
+    case 64: return slots == 1 ? launch_gemm_mode<64, false, 1>(p, pair, stream) : slots == 3 ? launch_gemm_mode<64, false, 3>(p, pair, stream) : launch_gemm_mode<64, false, 2>(p, pair, stream);
+    case 128: return slots == 1 ? launch_gemm_mode<128, false, 1>(p, pair, stream) : slots == 3 ? launch_gemm_mode<128, false, 3>(p, pair, stream) : launch_gemm_mode<128, false, 2>(p, pair, stream);
+    case 160: return slots == 1 ? launch_gemm_mode<160, false, 1>(p, pair, stream) : slots == 3 ? launch_gemm_mode<160, false, 3>(p, pair, stream) : launch_gemm_mode<160, false, 2>(p, pair, stream);
+    case 256: return launch_gemm_mode<256, false, 1>(p, pair, stream);
     default: set_error("unsupported BN %d (64/128/160/256)", bn); return -1;
   }
 }
@@ -562,6 +622,12 @@ static int fill_epilogue(GemmParams& p, const af_epilogue* ep, long long default
 
 using namespace af;
 
+extern "C" int af_gemm_set_pair_mode(int mode) {
+  const int old = g_pair_mode;
+  g_pair_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
+  return old;
+}
+
 extern "C" int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* A1, long long lda1, int K1,
                             const void* Wt, int M, int N, const af_epilogue* ep, int bn_hint, cudaStream_t stream) {
   AF_CHECK_ARG(A0 && Wt && ep, "af_gemm_bf16: null pointer");
@@ -574,6 +640,7 @@ extern "C" int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* 
   memset(&p, 0, sizeof(p));
   const int K = K0 + K1;
   const int bn = pick_bn(N, ep->geglu, bn_hint);
+  const bool pair = want_pair((M + 127) / 128, (N + bn - 1) / bn, bn, 0);
   AF_CHECK_ARG(!ep->geglu || N % 256 == 0, "geglu: packed N=%d must be a multiple of 256", N);
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K0), static_cast<uint64_t>(M)};
@@ -594,7 +661,7 @@ extern "C" int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* 
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
-    uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
+    uint32_t box[2] = {64, static_cast<uint32_t>(pair ? bn / 2 : bn)};
     int rc = make_tmap_bf16(&p.tmB, Wt, 2, dims, str, box);
     if (rc) return rc;
   }
@@ -610,7 +677,7 @@ extern "C" int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* 
   if (rc) return rc;
   rc = make_epilogue_maps(p, ep->geglu ? N / 2 : N, false);
   if (rc) return rc;
-  return dispatch_gemm(bn, p, stream);
+  return dispatch_gemm(bn, p, pair, stream);
 }
 
 // output-pixel box of one 128-row conv tile: bw = largest power of two <= min(64, next_pow2(Wo)); rows / images
@@ -646,6 +713,7 @@ extern "C" int af_conv3x3_bf16(const void* X0, int C0, const void* X1, int C1, c
   const int bn = pick_bn(Cout, 0, bn_hint);
   int bw, bh, nb;
   conv_tile_box(Ho, Wo, &bw, &bh, &nb);
+  const bool pair = want_pair(((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * ((B + nb - 1) / nb), (Cout + bn - 1) / bn, bn, 1);
   p.bw = bw; p.bh = bh; p.nb = nb;
   p.tiles_w = (Wo + bw - 1) / bw;
   p.tiles_h = (Ho + bh - 1) / bh;
@@ -683,7 +751,7 @@ extern "C" int af_conv3x3_bf16(const void* X0, int C0, const void* X1, int C1, c
     const uint64_t K = 9ull * Cin;
     uint64_t dims[2] = {K, static_cast<uint64_t>(Cout)};
     uint64_t str[1] = {K * 2};
-    uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
+    uint32_t box[2] = {64, static_cast<uint32_t>(pair ? bn / 2 : bn)};
     int rc = make_tmap_bf16(&p.tmB, Wt, 2, dims, str, box);
     if (rc) return rc;
   }
@@ -703,5 +771,5 @@ extern "C" int af_conv3x3_bf16(const void* X0, int C0, const void* X1, int C1, c
   }
   rc = make_epilogue_maps(p, Cout, true);
   if (rc) return rc;
-  return dispatch_gemm(bn, p, stream);
+  return dispatch_gemm(bn, p, pair, stream);
 }

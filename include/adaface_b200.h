@@ -67,6 +67,12 @@ typedef struct af_epilogue {
 int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* A1, long long lda1, int K1, const void* Wt,
                  int M, int N, const af_epilogue* ep, int bn_hint, af_stream_t stream);
 
+/* Tile schedule of af_gemm_bf16 / af_conv3x3_bf16: CTA pairs (tcgen05 cta_group::2: two SMs share one 256-row tile and
+ * each stages half of the weight tile) vs single-CTA 128-row tiles.  0 = never pair, 1 (default) = pair where it was
+ * measured to win (linear GEMMs, N tile >= 160, >= 2 waves), 2 = pair wherever legal.  Returns the previous mode.
+ * Results are bit-identical between the modes (same accumulation order). */
+int af_gemm_set_pair_mode(int mode);
+
 /* 3x3 convolution, pad 1, stride 1 or 2, NHWC bf16 input(s) [B,H,W,C0] (+ [B,H,W,C1] concat), weights
  * Wt[Cout][ky][kx][C0+C1] bf16, as an implicit GEMM (no im2col buffer).  Output rows are output pixels
  * (n, oh, ow) row-major.  Replaces nn.Conv2d 3x3 at openaimodel.py:155 (stride 2), :208, :234, :120-122. */

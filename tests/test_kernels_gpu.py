@@ -476,3 +476,54 @@ def test_linear_small_many_rows_and_tail_features():
         ops.linear_small(x, w, b, y, silu_in=True, silu_out=True)
         ref = F.silu(F.silu(x).double() @ w.double().t() + b.double()).float()
         assert _rel(y, ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ CTA pairs
+@pytest.mark.parametrize("M,N,K,res,bf16out", [(4096, 320, 320, True, False), (1000, 640, 2560, False, True),
+                                                (384, 1280, 768, True, True), (65536, 320, 320, True, False)])
+def test_gemm_pair_mode_matches_single_cta(M, N, K, res, bf16out):
+    """cta_group::2 (two SMs per 256-row tile) and single-CTA schedules accumulate in the same order: bit-identical."""
+    from adaprompt_b200 import _lib, ops
+    lib = _lib.load()
+    a = _rand(M, K, seed=1, dtype=torch.bfloat16)
+    w = _rand(N, K, seed=2, scale=K ** -0.5, dtype=torch.bfloat16)
+    bias = _rand(N, seed=3)
+    r = _rand(M, N, seed=4) if res else None
+    outs = []
+    for mode in (2, 0):
+        old = lib.af_gemm_set_pair_mode(mode)
+        try:
+            out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16 if bf16out else torch.float32)
+            ops.gemm(a, w, out, bias=bias, residual=r)
+            outs.append(out)
+        finally:
+            lib.af_gemm_set_pair_mode(old)
+    assert torch.equal(outs[0], outs[1])
+    ref = a.float() @ w.float().t() + bias + (r if res else 0)
+    assert _rel(outs[0], ref) < (4e-3 if bf16out else 2e-5)
+
+
+def test_conv_and_geglu_pair_mode_match_single_cta():
+    from adaprompt_b200 import _lib, ops
+    from adaprompt_b200.packing import pack_conv3x3, pack_geglu
+    lib = _lib.load()
+    x = _rand(3, 24, 24, 640, seed=1, dtype=torch.bfloat16)
+    w = pack_conv3x3(_rand(320, 640, 3, 3, seed=2, scale=(9 * 640) ** -0.5).to(torch.bfloat16))
+    res = _rand(3, 24, 24, 320, seed=5)
+    a = _rand(2048, 320, seed=3, dtype=torch.bfloat16)
+    wg, bg = pack_geglu(_rand(2560, 320, seed=4, scale=320 ** -0.5), _rand(2560, seed=6))
+    wg = wg.to(torch.bfloat16).contiguous()
+    outs = []
+    for mode in (2, 0):
+        old = lib.af_gemm_set_pair_mode(mode)
+        try:
+            o1 = torch.empty(3, 24, 24, 320, device=DEV)
+            st = ops.gn_stats_for_conv(3, 24, 24, 320, DEV)
+            ops.conv3x3(x, w, o1, residual=res, gn_stats=st.buf)
+            o2 = torch.empty(2048, 1280, device=DEV, dtype=torch.bfloat16)
+            ops.gemm(a, wg, o2, bias=bg, geglu=True)
+            outs.append((o1, st.buf.clone(), o2))
+        finally:
+            lib.af_gemm_set_pair_mode(old)
+    for u, v in zip(*outs):
+        assert torch.equal(u, v)
