@@ -298,7 +298,7 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample ---------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        med, times, cores = cpu_oracle_pair_seconds(2, 1)
+        med, times, cores = cpu_oracle_pair_seconds(6, 1)
         cpu_baseline = {"value": 1.0 / (DDIM_STEPS * med), "unit": "images/s", "cores": cores, "kind": "port",
                         "sample": f"{len(times)} x one CFG-pair UNet forward (batch 2, 64x64 latent, fp32 oracle), "
                                   f"median {med:.2f} s; one image = 50 such steps"}
