@@ -363,6 +363,9 @@ namespace af {
 int attention_pair_dispatch(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
                             int kv_stride, const unsigned char* key_mask, void* O, int B, int heads, int Nq, int Nk,
                             int d, cudaStream_t stream);  // attention_pair.cu
+int xattn_dispatch(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
+                   int kv_stride, const unsigned char* key_mask, void* O, int B, int heads, int Nq, int Nk, int d,
+                   cudaStream_t stream);  // xattn.cu
 }
 
 using namespace af;
@@ -377,6 +380,8 @@ extern "C" int af_attention_bf16(const void* Q, long long ldq, const void* K, lo
   AF_CHECK_ARG(ldvt >= 64, "af_attention_bf16: ldvt=%lld must be >= 64 (one 128-byte swizzle row)", ldvt);
   // TMA needs every box to start on a 16-byte boundary: sample b's keys start at column b*kv_stride of V^T
   AF_CHECK_ARG(B == 1 || kv_stride % 8 == 0, "af_attention_bf16: kv_stride=%d must be a multiple of 8 when B > 1", kv_stride);
+  if (Nq >= 256 && Nk <= 128 && (d == 40 || d == 80))    // short context, K / V resident per (sample, head) (xattn.cu)
+    return xattn_dispatch(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, B, heads, Nq, Nk, d, stream);
   if (Nq >= 256 && (d == 40 || (d == 80 && Nk <= 128)))  // two query tiles per CTA (attention_pair.cu)
     return attention_pair_dispatch(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, B, heads, Nq, Nk, d, stream);
   AttnParams p;

@@ -256,6 +256,14 @@ def test_self_attention_key_mask():
     assert _attn_case(2, 1024, 1024, 80, seed=7, mask=True) < 6e-3
 
 
+@pytest.mark.parametrize("B,N,Nk,d,mask", [(2, 2304, 77, 80, False), (1, 9216, 77, 40, False), (3, 300, 77, 40, True),
+                                           (2, 1024, 128, 80, True), (3, 512, 24, 40, False), (16, 4096, 77, 40, False),
+                                           (5, 384, 100, 80, False)])
+def test_short_context_attention(B, N, Nk, d, mask):
+    """xattn.cu: K / V resident per (sample, head), ragged query tiles, key masks, every key-count class."""
+    assert _attn_case(B, N, Nk, d, seed=31, mask=mask, cross=True) < 6e-3
+
+
 # ------------------------------------------------------------------------------------------------ norms
 @pytest.mark.parametrize("B,HW,C0,C1,eps,silu", [
     (2, 4096, 320, 0, 1e-5, True), (2, 1024, 640, 320, 1e-5, True), (3, 256, 1280, 640, 1e-5, True),
