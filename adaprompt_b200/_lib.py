@@ -35,6 +35,18 @@ class AfEpilogue(Structure):
     ]
 
 
+class AfBgemm(Structure):
+    _fields_ = [
+        ("A", c_void_p), ("lda", c_longlong), ("sA0", c_longlong), ("sA1", c_longlong),
+        ("B", c_void_p), ("ldb", c_longlong), ("sB0", c_longlong), ("sB1", c_longlong),
+        ("C", c_void_p), ("ldc", c_longlong), ("sC0", c_longlong), ("sC1", c_longlong), ("c_dtype", c_int),
+        ("vec", c_void_p), ("sV0", c_longlong), ("sV1", c_longlong),
+        ("P", c_void_p), ("ldp", c_longlong), ("sP0", c_longlong), ("sP1", c_longlong),
+        ("M", c_int), ("N", c_int), ("K", c_int), ("nb0", c_int), ("nb1", c_int), ("mode", c_int),
+        ("valid_rows", c_int), ("valid_cols", c_int), ("alpha", c_float),
+    ]
+
+
 # symbol -> (restype, argtypes); mirrors include/adaface_b200.h one to one
 SIGNATURES = {
     "af_version": (c_int, []),
@@ -77,6 +89,25 @@ SIGNATURES = {
     "af_splice_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "af_weighted_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_longlong,
                                 c_void_p]),
+    # ---- training step (backward kernels)
+    "af_attention_bf16_lse": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "af_bgemm_bf16": (c_int, [POINTER(AfBgemm), c_void_p]),
+    "af_groupnorm_bwd_workspace_floats": (c_size_t, [c_int, c_int, c_int]),
+    "af_groupnorm_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "af_layernorm_bwd": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_float, c_void_p, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p]),
+    "af_geglu_fwd": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
+    "af_geglu_bwd": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
+    "af_quick_gelu": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
+    "af_rowdot_heads": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "af_attention_small_bwd": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_longlong, c_void_p, c_int,
+                                       c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "af_conv_out_dgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "af_sumpool2x2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "af_zero_insert2x": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "af_transpose_to_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_void_p, c_void_p]),
 }
 
 _lib = None
@@ -116,6 +147,9 @@ KERNELS_PER_CALL = {
     "af_weighted_sum": 1, "af_layernorm_f32": 1,
     "af_conv_in": 1, "af_conv_out": 1, "af_timestep_embedding": 1, "af_linear_small": 1, "af_cast_bf16": 1,
     "af_upsample2x_cast": 1, "af_cfg_ddim_update": 1, "af_advance_step": 1,
+    "af_attention_bf16_lse": 1, "af_bgemm_bf16": 1, "af_groupnorm_bwd": 3, "af_layernorm_bwd": 1, "af_geglu_fwd": 1,
+    "af_geglu_bwd": 1, "af_quick_gelu": 1, "af_rowdot_heads": 1, "af_attention_small_bwd": 1, "af_conv_out_dgrad": 1,
+    "af_sumpool2x2": 1, "af_zero_insert2x": 1, "af_transpose_to_bf16": 1,
 }
 
 

@@ -27,6 +27,7 @@
 namespace af {
 
 struct AttnParams {
+  float* lse;        // optional [B][heads][Nq]: log2-sum-exp of every query row (training: recomputation of P)
   CUtensorMap tmQ;   // 3-D {ldq, Nq, B}, box {64, 128, 1}
   CUtensorMap tmK;   // 3-D {ldk, Nk, B}, box {64, BLOCK_N, 1}
   CUtensorMap tmV;   // 2-D {total keys, 8*d}, box {64, DV}
@@ -313,6 +314,8 @@ __global__ void __launch_bounds__(192, 1) attention_kernel(const __grid_constant
     mbar_wait(pv_done, pvph);
     tc_fence_after();
     const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
+    if (p.lse != nullptr && q_row < p.Nq)
+      p.lse[(static_cast<size_t>(b) * p.heads + h) * p.Nq + q_row] = l_run > 0.f ? m_run + __log2f(l_run) : INFINITY;
     __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * p.Nq + q_row) * p.ldo + h * p.d;
 #pragma unroll 1
     for (int c = 0; c < DV; c += 16) {
@@ -362,17 +365,27 @@ static int launch_attention(const AttnParams& p, cudaStream_t stream) {
 namespace af {
 int attention_pair_dispatch(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
                             int kv_stride, const unsigned char* key_mask, void* O, int B, int heads, int Nq, int Nk,
-                            int d, cudaStream_t stream);  // attention_pair.cu
+                            int d, float* lse, cudaStream_t stream);  // attention_pair.cu
 int xattn_dispatch(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
                    int kv_stride, const unsigned char* key_mask, void* O, int B, int heads, int Nq, int Nk, int d,
-                   cudaStream_t stream);  // xattn.cu
+                   float* lse, cudaStream_t stream);  // xattn.cu
 }
 
 using namespace af;
 
+extern "C" int af_attention_bf16_lse(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt,
+                                     long long ldvt, int kv_stride, const unsigned char* key_mask, void* O, float* lse,
+                                     int B, int heads, int Nq, int Nk, int d, cudaStream_t stream);
+
 extern "C" int af_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt,
                                  long long ldvt, int kv_stride, const unsigned char* key_mask, void* O, int B,
                                  int heads, int Nq, int Nk, int d, cudaStream_t stream) {
+  return af_attention_bf16_lse(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, nullptr, B, heads, Nq, Nk, d, stream);
+}
+
+extern "C" int af_attention_bf16_lse(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt,
+                                     long long ldvt, int kv_stride, const unsigned char* key_mask, void* O, float* lse,
+                                     int B, int heads, int Nq, int Nk, int d, cudaStream_t stream) {
   AF_CHECK_ARG(Q && K && Vt && O, "af_attention_bf16: null pointer");
   AF_CHECK_ARG(d == 40 || d == 80 || d == 160, "af_attention_bf16: head dim %d unsupported (40/80/160)", d);
   AF_CHECK_ARG(B > 0 && heads > 0 && Nq > 0 && Nk > 0 && kv_stride >= Nk, "af_attention_bf16: bad sizes");
@@ -381,9 +394,9 @@ extern "C" int af_attention_bf16(const void* Q, long long ldq, const void* K, lo
   // TMA needs every box to start on a 16-byte boundary: sample b's keys start at column b*kv_stride of V^T
   AF_CHECK_ARG(B == 1 || kv_stride % 8 == 0, "af_attention_bf16: kv_stride=%d must be a multiple of 8 when B > 1", kv_stride);
   if (Nq >= 256 && Nk <= 128 && (d == 40 || d == 80))    // short context, K / V resident per (sample, head) (xattn.cu)
-    return xattn_dispatch(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, B, heads, Nq, Nk, d, stream);
+    return xattn_dispatch(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, B, heads, Nq, Nk, d, lse, stream);
   if (Nq >= 256 && (d == 40 || (d == 80 && Nk <= 128)))  // two query tiles per CTA (attention_pair.cu)
-    return attention_pair_dispatch(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, B, heads, Nq, Nk, d, stream);
+    return attention_pair_dispatch(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, B, heads, Nq, Nk, d, lse, stream);
   AttnParams p;
   memset(&p, 0, sizeof(p));
   const int dp = d == 40 ? 48 : d;
@@ -416,6 +429,7 @@ extern "C" int af_attention_bf16(const void* Q, long long ldq, const void* K, lo
   }
   p.B = B; p.heads = heads; p.Nq = Nq; p.Nk = Nk; p.d = d; p.dp = dp; p.vt_stride = kv_stride;
   p.key_mask = key_mask;
+  p.lse = lse;
   p.out = static_cast<__nv_bfloat16*>(O);
   p.ldo = static_cast<long long>(heads) * d;
   switch (d) {

@@ -28,6 +28,7 @@
 namespace af {
 
 struct AttnPairParams {
+  float* lse;        // optional [B][heads][Nq] log2-sum-exp per query row
   CUtensorMap tmQ;   // 3-D {heads*dp, Nq, B}, box {64, 128, 1}
   CUtensorMap tmK;   // 3-D {heads*dp, Nk, B}, box {64, BLOCK_N, 1}
   CUtensorMap tmV;   // 2-D {ldvt, heads*d}, box {64, DV}
@@ -369,6 +370,8 @@ __global__ void __launch_bounds__(384, 1) attention_pair_kernel(const __grid_con
     mbar_wait(&pv_done[t], (n_blocks - 1) & 1);
     tc_fence_after();
     const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
+    if (p.lse != nullptr && q_row < p.Nq)
+      p.lse[(static_cast<size_t>(b) * p.heads + h) * p.Nq + q_row] = l_run > 0.f ? m_ref + __log2f(l_run) : INFINITY;
     __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * p.Nq + q_row) * p.ldo + h * p.d;
 #pragma unroll 1
     for (int c = 0; c < DV; c += 16) {
@@ -416,7 +419,7 @@ static int launch_pair(const AttnPairParams& p, cudaStream_t stream) {
 // Called by af_attention_bf16 (attention.cu) for d in {40, 80} when Nq >= 256.  Returns -100 if unsupported.
 int attention_pair_dispatch(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
                             int kv_stride, const unsigned char* key_mask, void* O, int B, int heads, int Nq, int Nk,
-                            int d, cudaStream_t stream) {
+                            int d, float* lse, cudaStream_t stream) {
   if (!(d == 40 || d == 80)) return -100;
   AttnPairParams p;
   memset(&p, 0, sizeof(p));
@@ -445,6 +448,7 @@ int attention_pair_dispatch(const void* Q, long long ldq, const void* K, long lo
   }
   p.B = B; p.heads = heads; p.Nq = Nq; p.Nk = Nk; p.d = d; p.dp = dp; p.kv_stride = kv_stride;
   p.key_mask = key_mask;
+  p.lse = lse;
   p.out = static_cast<__nv_bfloat16*>(O);
   p.ldo = static_cast<long long>(heads) * d;
   return d == 40 ? launch_pair<40>(p, stream) : launch_pair<80>(p, stream);

@@ -22,6 +22,7 @@
 namespace af {
 
 struct XAttnParams {
+  float* lse;        // optional [B][heads][Nq] log2-sum-exp per query row
   CUtensorMap tmQ;   // 3-D {heads*dp, Nq, B}, box {64, 128, 1}
   CUtensorMap tmK;   // 3-D {heads*dp, Nk, B}, box {64, 128, 1}
   CUtensorMap tmV;   // 2-D {ldvt, heads*d}, box {64, DV}
@@ -260,6 +261,8 @@ __global__ void __launch_bounds__(320, 1) xattn_kernel(const __grid_constant__ X
       const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
       const int q_row = (tile0 + i) * 128 + r;
       __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * p.Nq + q_row) * p.ldo + h * p.d;
+      if (p.lse != nullptr && q_row < p.Nq)
+        p.lse[(static_cast<size_t>(b) * p.heads + h) * p.Nq + q_row] = l_run > 0.f ? m_use + __log2f(l_run) : INFINITY;
       mbar_wait(&pv_done[w], par);
       tc_fence_after();
 #pragma unroll
@@ -344,7 +347,7 @@ static int launch_xattn(XAttnParams& p, cudaStream_t stream) {
 // Called by af_attention_bf16 (attention.cu) for d in {40, 80}, Nk <= 128.  Returns -100 if unsupported.
 int xattn_dispatch(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
                    int kv_stride, const unsigned char* key_mask, void* O, int B, int heads, int Nq, int Nk, int d,
-                   cudaStream_t stream) {
+                   float* lse, cudaStream_t stream) {
   if (!(d == 40 || d == 80) || Nk > 128) return -100;
   XAttnParams p;
   memset(&p, 0, sizeof(p));
@@ -372,6 +375,7 @@ int xattn_dispatch(const void* Q, long long ldq, const void* K, long long ldk, c
   }
   p.B = B; p.heads = heads; p.Nq = Nq; p.Nk = Nk; p.d = d; p.dp = dp; p.kv_stride = kv_stride;
   p.key_mask = key_mask;
+  p.lse = lse;
   p.out = static_cast<__nv_bfloat16*>(O);
   p.ldo = static_cast<long long>(heads) * d;
   return d == 40 ? launch_xattn<40>(p, stream) : launch_xattn<80>(p, stream);

@@ -426,3 +426,186 @@ def weighted_sum(a: torch.Tensor, b: torch.Tensor, c: Optional[torch.Tensor], w,
                              out.data_ptr(), a.numel(), _stream())
     _lib.check(rc, "af_weighted_sum")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# training step: backward kernels (train.cu, bgemm.cu)
+# ---------------------------------------------------------------------------------------------------
+def attention_lse(q, k, vt, out, lse, *, B, heads, Nq, Nk, d, ldq, ldk, ldvt, kv_stride, key_mask=None):
+    """af_attention_bf16 that also writes lse fp32 [B, heads, Nq] (log2-sum-exp of each query row)."""
+    lib = _lib.load()
+    _chk(lse, torch.float32, "lse")
+    if key_mask is not None:
+        _chk(key_mask, torch.uint8, "key_mask")
+    rc = lib.af_attention_bf16_lse(q.data_ptr(), ldq, k.data_ptr(), ldk, vt.data_ptr(), ldvt, kv_stride, _p(key_mask),
+                                   out.data_ptr(), lse.data_ptr(), B, heads, Nq, Nk, d, _stream())
+    _lib.check(rc, "af_attention_bf16_lse")
+    return out
+
+
+def bgemm(A, lda, sA, Bm, ldb, sB, C, ldc, sC, *, M, N, K, nb0, nb1, mode=0, vec=None, sV=(0, 0), P=None, ldp=0,
+          sP=(0, 0), valid_rows=0, valid_cols=0, alpha=1.0):
+    """Batched strided C[z] = epi(A[z] . B[z]^T); A/B/C/P are (tensor, element offset) pairs or tensors."""
+    lib = _lib.load()
+
+    def ptr(t):
+        if isinstance(t, tuple):
+            return t[0].data_ptr() + t[1] * t[0].element_size()
+        return t.data_ptr()
+
+    Ct = C[0] if isinstance(C, tuple) else C
+    g = _lib.AfBgemm()
+    g.A, g.lda, g.sA0, g.sA1 = ptr(A), lda, sA[0], sA[1]
+    g.B, g.ldb, g.sB0, g.sB1 = ptr(Bm), ldb, sB[0], sB[1]
+    g.C, g.ldc, g.sC0, g.sC1 = ptr(C), ldc, sC[0], sC[1]
+    g.c_dtype = AF_DTYPE_F32 if Ct.dtype == torch.float32 else AF_DTYPE_BF16
+    g.vec, g.sV0, g.sV1 = (vec.data_ptr() if vec is not None else None), sV[0], sV[1]
+    g.P, g.ldp, g.sP0, g.sP1 = (ptr(P) if P is not None else None), ldp, sP[0], sP[1]
+    g.M, g.N, g.K, g.nb0, g.nb1, g.mode = M, N, K, nb0, nb1, mode
+    g.valid_rows, g.valid_cols, g.alpha = valid_rows, valid_cols, float(alpha)
+    rc = lib.af_bgemm_bf16(byref(g), _stream())
+    _lib.check(rc, "af_bgemm_bf16")
+
+
+def groupnorm_mean_rstd(x: torch.Tensor, st: GNStats, eps: float) -> torch.Tensor:
+    """mean / rstd [B, 32, 2] of a single-source GroupNorm from its partial statistics."""
+    lib = _lib.load()
+    B, C = int(x.shape[0]), int(x.shape[-1])
+    HW = x.numel() // (B * C)
+    mr = torch.empty(B * 64, dtype=torch.float32, device=x.device)
+    rc = lib.af_groupnorm_finalize(st.buf.data_ptr(), C, st.slots, None, 0, 0, B, HW, float(eps), mr.data_ptr(), _stream())
+    _lib.check(rc, "af_groupnorm_finalize")
+    return mr
+
+
+def groupnorm_apply_mr(x: torch.Tensor, mr: torch.Tensor, gamma, beta, silu: bool, out: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    B, C = int(x.shape[0]), int(x.shape[-1])
+    HW = x.numel() // (B * C)
+    rc = lib.af_groupnorm_apply(x.data_ptr(), C, None, 0, B, HW, mr.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                1 if silu else 0, out.data_ptr(), None, _stream())
+    _lib.check(rc, "af_groupnorm_apply")
+    return out
+
+
+def groupnorm_bwd(x, mr, gamma, beta, silu: bool, dy: torch.Tensor, dres: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(x, torch.float32, "x")
+    _chk(dy, torch.bfloat16, "dy")
+    if dres is not None:
+        _chk(dres, torch.float32, "dres")
+    B, C = int(x.shape[0]), int(x.shape[-1])
+    HW = x.numel() // (B * C)
+    ws = torch.empty(lib.af_groupnorm_bwd_workspace_floats(B, C, HW), dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x)
+    rc = lib.af_groupnorm_bwd(x.data_ptr(), C, B, HW, mr.data_ptr(), gamma.data_ptr(), beta.data_ptr(), int(silu),
+                              dy.data_ptr(), _p(dres), dx.data_ptr(), ws.data_ptr(), _stream())
+    _lib.check(rc, "af_groupnorm_bwd")
+    return dx
+
+
+def layernorm_bwd(x, gamma, eps, dy, dres=None, dgamma=None, dbeta=None) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(x, torch.float32, "x")
+    if not dy.is_contiguous() or dy.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("dy must be contiguous fp32 / bf16")
+    C = int(x.shape[-1])
+    dx = torch.empty_like(x)
+    rc = lib.af_layernorm_bwd(x.data_ptr(), x.numel() // C, C, gamma.data_ptr(), float(eps), dy.data_ptr(),
+                              AF_DTYPE_F32 if dy.dtype == torch.float32 else AF_DTYPE_BF16, _p(dres), dx.data_ptr(),
+                              _p(dgamma), _p(dbeta), _stream())
+    _lib.check(rc, "af_layernorm_bwd")
+    return dx
+
+
+def geglu_fwd(proj: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(proj, torch.bfloat16, "proj")
+    T, F2 = int(proj.shape[0]), int(proj.shape[1])
+    h = torch.empty(T, F2 // 2, dtype=torch.bfloat16, device=proj.device)
+    _lib.check(lib.af_geglu_fwd(proj.data_ptr(), T, F2 // 2, h.data_ptr(), _stream()), "af_geglu_fwd")
+    return h
+
+
+def geglu_bwd(proj: torch.Tensor, dh: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(proj, torch.bfloat16, "proj")
+    _chk(dh, torch.bfloat16, "dh")
+    T, F2 = int(proj.shape[0]), int(proj.shape[1])
+    dproj = torch.empty_like(proj)
+    _lib.check(lib.af_geglu_bwd(proj.data_ptr(), dh.data_ptr(), T, F2 // 2, dproj.data_ptr(), _stream()), "af_geglu_bwd")
+    return dproj
+
+
+def quick_gelu(x: torch.Tensor, dy: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(x, torch.bfloat16, "x")
+    if dy is not None:
+        _chk(dy, torch.bfloat16, "dy")
+    out = torch.empty_like(x)
+    _lib.check(lib.af_quick_gelu(x.data_ptr(), _p(dy), x.numel(), out.data_ptr(), _stream()), "af_quick_gelu")
+    return out
+
+
+def rowdot_heads(a: torch.Tensor, b: torch.Tensor, B: int, N: int, heads: int, d: int) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(a, torch.bfloat16, "a")
+    _chk(b, torch.bfloat16, "b")
+    delta = torch.empty(B, heads, N, dtype=torch.float32, device=a.device)
+    _lib.check(lib.af_rowdot_heads(a.data_ptr(), b.data_ptr(), B, N, heads, d, delta.data_ptr(), _stream()), "af_rowdot_heads")
+    return delta
+
+
+def attention_small_bwd(qkv, dout, *, B, heads, L, k_off, v_off, mult=1, scale=0.125, causal=True) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(qkv, torch.bfloat16, "qkv")
+    _chk(dout, torch.bfloat16, "dout")
+    dqkv = torch.zeros_like(qkv)
+    rc = lib.af_attention_small_bwd(qkv.data_ptr(), int(qkv.stride(0)), int(k_off), int(v_off), dout.data_ptr(),
+                                    int(dout.stride(0)), dqkv.data_ptr(), B, heads, L, mult, float(scale), int(causal),
+                                    _stream())
+    _lib.check(rc, "af_attention_small_bwd")
+    return dqkv
+
+
+def conv_out_dgrad(dout_nchw: torch.Tensor, w: torch.Tensor, C: int) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(dout_nchw, torch.float32, "dout")
+    _chk(w, torch.float32, "w")
+    B, Cout, H, W = (int(v) for v in dout_nchw.shape)
+    dy = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=dout_nchw.device)
+    _lib.check(lib.af_conv_out_dgrad(dout_nchw.data_ptr(), w.data_ptr(), B, H, W, C, Cout, dy.data_ptr(), _stream()),
+               "af_conv_out_dgrad")
+    return dy
+
+
+def sumpool2x2(x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(x, torch.float32, "x")
+    B, H2, W2, C = (int(v) for v in x.shape)
+    out = torch.empty(B, H2 // 2, W2 // 2, C, dtype=torch.float32, device=x.device)
+    _lib.check(lib.af_sumpool2x2(x.data_ptr(), B, H2 // 2, W2 // 2, C, out.data_ptr(), _stream()), "af_sumpool2x2")
+    return out
+
+
+def zero_insert2x(x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(x, torch.float32, "x")
+    B, H, W, C = (int(v) for v in x.shape)
+    out = torch.empty(B, 2 * H, 2 * W, C, dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.af_zero_insert2x(x.data_ptr(), B, H, W, C, out.data_ptr(), _stream()), "af_zero_insert2x")
+    return out
+
+
+def transpose_to_bf16(x: torch.Tensor, ldo: Optional[int] = None) -> torch.Tensor:
+    """x [R, C] fp32 | bf16 -> bf16 [C, ldo] (ldo = R rounded up to 8), zero padded."""
+    lib = _lib.load()
+    if x.dtype not in (torch.float32, torch.bfloat16) or not x.is_contiguous():
+        raise ValueError("transpose_to_bf16: contiguous fp32 / bf16 expected")
+    R, C = int(x.shape[0]), int(x.shape[1])
+    ldo = (R + 7) // 8 * 8 if ldo is None else ldo
+    out = torch.empty(C, ldo, dtype=torch.bfloat16, device=x.device)
+    rc = lib.af_transpose_to_bf16(x.data_ptr(), AF_DTYPE_F32 if x.dtype == torch.float32 else AF_DTYPE_BF16, R, C, ldo,
+                                  out.data_ptr(), _stream())
+    _lib.check(rc, "af_transpose_to_bf16")
+    return out

@@ -90,6 +90,12 @@ int af_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk
                       int kv_stride, const unsigned char* key_mask, void* O, int B, int heads, int Nq, int Nk, int d,
                       af_stream_t stream);
 
+/* Same, also writing lse [B][heads][Nq] fp32 = log2-sum-exp of every query row (in the exp2 domain of the pre-scaled
+ * scores) when lse != NULL: the backward pass recomputes P = exp2(S - lse) from it (training step). */
+int af_attention_bf16_lse(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
+                          int kv_stride, const unsigned char* key_mask, void* O, float* lse, int B, int heads, int Nq,
+                          int Nk, int d, af_stream_t stream);
+
 /* GroupNorm(32) over the channel concat [x0 | x1] of fp32 NHWC tensors, optional SiLU, bf16 output
  * [B, HW, C0+C1]; optional raw bf16 copy of the concat (operand of the 1x1 skip conv).
  * Replaces GroupNorm32+SiLU (util.py:217-219; openaimodel.py:205-207,229-231,693-695) and Normalize
@@ -170,6 +176,57 @@ int af_splice_rows(float* dst, const float* src, const int* start, const int* sr
  * evaluated as ((w0*a + w1*b) + w2*c) like (stack * w).sum(0). */
 int af_weighted_sum(const float* a, const float* b, const float* c, float w0, float w1, float w2, float* out,
                     long long n, af_stream_t stream);
+
+/* ---- Stage-1 distillation step: backward kernels.  The reference gets these from
+ * torch.autograd over the modules cited above (guided_denoise ddpm.py:2483-2532 -> UNetModel.forward with grad; UNet
+ * weights frozen ddpm.py:783-786).  dgrad GEMMs / convolutions reuse af_gemm_bf16 / af_conv3x3_bf16 on transposed
+ * weight packs; the entry points below are the remaining pieces. ---- */
+
+/* Batched strided C[z] = epi(A[z][M,K] . B[z][N,K]^T), z = b0*nb1 + b1, bf16 operands, fp32 accumulate
+ * (mma.sync tiles; attention backward per (sample, head): autograd of attention.py:198-242).
+ * mode 0: alpha*acc | 1: exp2(acc - vec[row]) | 2: exp2(acc - vec[col]) | 3: alpha*P[row,col]*(acc - vec[row]) |
+ * 4: alpha*P[row,col]*(acc - vec[col]).  Entries with row >= valid_rows or col >= valid_cols are written as 0.
+ * All strides in elements; operand pitches / batch strides multiples of 8, K % 8 == 0, N even. */
+typedef struct af_bgemm {
+  const void* A; long long lda, sA0, sA1;
+  const void* B; long long ldb, sB0, sB1;
+  void* C; long long ldc, sC0, sC1; int c_dtype;
+  const float* vec; long long sV0, sV1;
+  const void* P; long long ldp, sP0, sP1;
+  int M, N, K, nb0, nb1, mode, valid_rows, valid_cols;
+  float alpha;
+} af_bgemm;
+int af_bgemm_bf16(const af_bgemm* g, af_stream_t stream);
+
+/* GroupNorm(32)(+SiLU) backward w.r.t. the fp32 input: x [B,HW,C], mean_rstd [B,32,2] (af_groupnorm_finalize),
+ * dy bf16 [B,HW,C] (gradient of the bf16 output), dres fp32 or NULL (added: gradient of a residual branch), dx fp32.
+ * workspace: af_groupnorm_bwd_workspace_floats(B, C, HW) floats.  Deterministic. */
+size_t af_groupnorm_bwd_workspace_floats(int B, int C, int HW);
+int af_groupnorm_bwd(const float* x, int C, int B, int HW, const float* mean_rstd, const float* gamma, const float* beta,
+                     int silu, const void* dy_bf16, const float* dres, float* dx, float* workspace, af_stream_t stream);
+/* nn.LayerNorm backward: dx = LN'(x)^T dy (+ dres); dy bf16 or fp32 (dy_dtype); dgamma / dbeta (both or neither) are
+ * ACCUMULATED with fp32 atomics (trainable CLIP text LayerNorms of SubjBasisGenerator.prompt2token_proj). */
+int af_layernorm_bwd(const float* x, long long rows, int C, const float* gamma, float eps, const void* dy, int dy_dtype,
+                     const float* dres, float* dx, float* dgamma, float* dbeta, af_stream_t stream);
+/* GEGLU in its unfused training form (attention.py:32-39): proj bf16 [T,2F] = (value | gate) -> h bf16 [T,F]. */
+int af_geglu_fwd(const void* proj, long long T, int F, void* h, af_stream_t stream);
+int af_geglu_bwd(const void* proj, const void* dh, long long T, int F, void* dproj, af_stream_t stream);
+/* quick_gelu: out = x*sigmoid(1.702x) (dy NULL) or its derivative times dy; bf16. */
+int af_quick_gelu(const void* x, const void* dy, long long n, void* out, af_stream_t stream);
+/* delta[b][h][q] = sum_c a[b,q,h*d+c] * b[b,q,h*d+c] (rowsum(dO o O) of the softmax backward); a, b bf16 [B*N, heads*d]. */
+int af_rowdot_heads(const void* a, const void* b, int B, int N, int heads, int d, float* delta, af_stream_t stream);
+/* backward of af_attention_small: dqkv bf16 in the layout of qkv, from dout bf16 [B*L, ldo]. */
+int af_attention_small_bwd(const void* qkv, long long ldq, int k_off, int v_off, const void* dout, long long ldo,
+                           void* dqkv, int B, int heads, int L, int mult, float scale, int causal, af_stream_t stream);
+/* dgrad of UNetModel.out[2] (openaimodel.py:696): dout NCHW fp32 [B,Cout,H,W], w fp32 [Cout,C,3,3] -> dy bf16 NHWC. */
+int af_conv_out_dgrad(const float* dout_nchw, const float* w, int B, int H, int W, int C, int Cout, void* dy_bf16,
+                      af_stream_t stream);
+/* backward of nearest x2 upsampling (openaimodel.py:120): in fp32 [B,2H,2W,C] -> out [B,H,W,C] (2x2 sums). */
+int af_sumpool2x2(const float* in, int B, int H, int W, int C, float* out, af_stream_t stream);
+/* operand of the stride-2 conv dgrad (openaimodel.py:155): in fp32 [B,H,W,C] -> out bf16 [B,2H,2W,C], zeros inserted. */
+int af_zero_insert2x(const float* in, int B, int H, int W, int C, void* out_bf16, af_stream_t stream);
+/* out bf16 [C][ldo] = in[R][C]^T (in fp32 or bf16), zero padded to ldo columns: weight-gradient GEMM operands. */
+int af_transpose_to_bf16(const void* in, int in_dtype, int R, int C, long long ldo, void* out_bf16, af_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,297 @@
+"""Stage-1 training step on a B200: every backward kernel against torch.autograd of a
+plain fp32 PyTorch restatement of the same op, then the whole UNet's gradient w.r.t. the layerwise context against
+autograd through the CPU oracle (oracle/unet_oracle.py, the pinned restatement of UNetModel.forward).
+All calls go through the C ABI (adaprompt_b200.ops / adaprompt_b200.train -> ctypes -> libadaface_b200.so)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def _rand(*shape, seed=0, scale=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+# ------------------------------------------------------------------------------------------------ bgemm
+@pytest.mark.parametrize("M,N,K,nb0,nb1", [(256, 80, 48, 2, 3), (200, 136, 40, 1, 2), (80, 48, 256, 2, 2), (64, 64, 64, 1, 1)])
+def test_bgemm_plain_strided(M, N, K, nb0, nb1):
+    from adaprompt_b200 import ops
+    a = _rand(nb0, M, nb1, K, seed=1, dtype=torch.bfloat16)           # [b0][row][b1][k]: head-sliced layout
+    b = _rand(nb0, N, nb1, K, seed=2, dtype=torch.bfloat16)
+    c = torch.full((nb0, nb1, M, N), 7.0, device=DEV, dtype=torch.float32)
+    ops.bgemm(a, nb1 * K, (M * nb1 * K, K), b, nb1 * K, (N * nb1 * K, K), c, N, (nb1 * M * N, M * N), M=M, N=N, K=K,
+              nb0=nb0, nb1=nb1, alpha=0.5)
+    ref = 0.5 * torch.einsum("bmhk,bnhk->bhmn", a.float(), b.float())
+    assert _rel(c, ref) < 1e-5
+
+
+def test_bgemm_softmax_epilogues():
+    from adaprompt_b200 import ops
+    M, N, K, nb0, nb1, vr, vc = 192, 80, 48, 2, 2, 192, 77
+    a = _rand(nb0, nb1, M, K, seed=3, dtype=torch.bfloat16)
+    b = _rand(nb0, nb1, N, K, seed=4, dtype=torch.bfloat16)
+    s = torch.einsum("bhmk,bhnk->bhmn", a.float(), b.float())
+    rowv = _rand(nb0, nb1, M, seed=5)
+    P = torch.empty(nb0, nb1, M, N, device=DEV, dtype=torch.bfloat16)
+    sA, sB, sC = (nb1 * M * K, M * K), (nb1 * N * K, N * K), (nb1 * M * N, M * N)
+    ops.bgemm(a, K, sA, b, K, sB, P, N, sC, M=M, N=N, K=K, nb0=nb0, nb1=nb1, mode=1, vec=rowv, sV=(nb1 * M, M),
+              valid_rows=vr, valid_cols=vc)
+    ref = torch.exp2(s - rowv[..., None])
+    ref[..., vc:] = 0
+    assert _rel(P, ref) < 4e-3
+    # transposed problem with a column vector, then the dS epilogue on top of it
+    Pt = torch.empty(nb0, nb1, N, M, device=DEV, dtype=torch.bfloat16)
+    ops.bgemm(b, K, sB, a, K, sA, Pt, M, sC, M=N, N=M, K=K, nb0=nb0, nb1=nb1, mode=2, vec=rowv, sV=(nb1 * M, M),
+              valid_rows=vc, valid_cols=vr)
+    assert _rel(Pt, ref.transpose(2, 3)) < 4e-3
+    dS = torch.empty(nb0, nb1, M, N, device=DEV, dtype=torch.float32)
+    ops.bgemm(a, K, sA, b, K, sB, dS, N, sC, M=M, N=N, K=K, nb0=nb0, nb1=nb1, mode=3, vec=rowv, sV=(nb1 * M, M), P=P,
+              ldp=N, sP=sC, valid_cols=vc, alpha=0.7)
+    ref3 = 0.7 * P.float() * (s - rowv[..., None])
+    ref3[..., vc:] = 0
+    assert _rel(dS, ref3) < 1e-4
+    dSt = torch.empty(nb0, nb1, N, M, device=DEV, dtype=torch.float32)
+    ops.bgemm(b, K, sB, a, K, sA, dSt, M, sC, M=N, N=M, K=K, nb0=nb0, nb1=nb1, mode=4, vec=rowv, sV=(nb1 * M, M), P=Pt,
+              ldp=M, sP=sC, valid_rows=vc, alpha=0.7)
+    ref4 = 0.7 * Pt.float() * (s.transpose(2, 3) - rowv[:, :, None, :])
+    ref4[:, :, vc:] = 0
+    assert _rel(dSt, ref4) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ norms / activations
+@pytest.mark.parametrize("B,HW,C,silu,eps", [(2, 256, 320, True, 1e-5), (3, 64, 1280, True, 1e-5), (2, 1024, 640, False, 1e-6),
+                                             (1, 4096, 960, True, 1e-5)])
+def test_groupnorm_backward(B, HW, C, silu, eps):
+    from adaprompt_b200.train import GroupNormFn
+    x = (_rand(B, HW, C, seed=1) * 2 + 0.3).requires_grad_(True)
+    g, b = _rand(C, seed=2) * 0.5 + 1.0, _rand(C, seed=3) * 0.2
+    dy = _rand(B, HW, C, seed=4, dtype=torch.bfloat16)
+    y = GroupNormFn.apply(x, g, b, eps, silu)
+    y.backward(dy)
+    xr = x.detach().clone().requires_grad_(True)
+    yr = F.group_norm(xr.permute(0, 2, 1), 32, g, b, eps).permute(0, 2, 1)
+    if silu:
+        yr = F.silu(yr)
+    yr.backward(dy.float())
+    assert _rel(y, yr) < 4e-3
+    assert _rel(x.grad, xr.grad) < 2e-4
+
+
+@pytest.mark.parametrize("rows,C,dt", [(512, 320, torch.bfloat16), (100, 1280, torch.bfloat16), (308, 768, torch.float32)])
+def test_layernorm_backward_with_param_grads(rows, C, dt):
+    from adaprompt_b200.train import LayerNormFn
+    x = _rand(rows, C, seed=1).requires_grad_(True)
+    g = (_rand(C, seed=2) * 0.5 + 1.0).requires_grad_(True)
+    b = (_rand(C, seed=3) * 0.2).requires_grad_(True)
+    dy = _rand(rows, C, seed=4, dtype=dt)
+    LayerNormFn.apply(x, g, b, 1e-5, dt).backward(dy)
+    xr, gr, br = (t.detach().clone().requires_grad_(True) for t in (x, g, b))
+    F.layer_norm(xr, (C,), gr, br, 1e-5).backward(dy.float())
+    assert _rel(x.grad, xr.grad) < 1e-4
+    assert _rel(g.grad, gr.grad) < 1e-4
+    assert _rel(b.grad, br.grad) < 1e-4
+
+
+def test_geglu_and_quick_gelu_backward():
+    from adaprompt_b200 import ops
+    from adaprompt_b200.train import GegluFn
+    proj = _rand(300, 2 * 640, seed=1, dtype=torch.bfloat16).requires_grad_(True)
+    dh = _rand(300, 640, seed=2, dtype=torch.bfloat16)
+    h = GegluFn.apply(proj)
+    h.backward(dh)
+    pr = proj.detach().float().requires_grad_(True)
+    a, gate = pr.chunk(2, dim=-1)
+    hr = a * F.gelu(gate)
+    hr.backward(dh.float())
+    assert _rel(h, hr) < 4e-3
+    assert _rel(proj.grad, pr.grad) < 5e-3
+    x = _rand(77, 3072, seed=3, dtype=torch.bfloat16)
+    dy = _rand(77, 3072, seed=4, dtype=torch.bfloat16)
+    xr = x.float().requires_grad_(True)
+    yr = xr * torch.sigmoid(1.702 * xr)
+    yr.backward(dy.float())
+    assert _rel(ops.quick_gelu(x), yr) < 4e-3
+    assert _rel(ops.quick_gelu(x, dy), xr.grad) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ linear / conv
+def test_linear_dgrad_and_wgrad():
+    from adaprompt_b200.train import linear
+    T, K, N = 308, 768, 3072
+    x = _rand(T, K, seed=1, dtype=torch.bfloat16).requires_grad_(True)
+    w = (_rand(N, K, seed=2) * 0.05).requires_grad_(True)
+    b = _rand(N, seed=3).requires_grad_(True)
+    res = _rand(T, N, seed=5).requires_grad_(True)
+    wb = w.detach().to(torch.bfloat16).contiguous()
+    dy = _rand(T, N, seed=4)
+    out = linear(x, wb, wb.t().contiguous(), b.detach(), residual=res, w_param=w, b_param=b)
+    out.backward(dy)
+    xr = x.detach().float().requires_grad_(True)
+    wr = wb.float().requires_grad_(True)
+    br, rr = b.detach().clone().requires_grad_(True), res.detach().clone().requires_grad_(True)
+    (xr @ wr.t() + br + rr).backward(dy)
+    assert _rel(x.grad, xr.grad) < 6e-3          # bf16 dY operand + bf16 result
+    assert _rel(w.grad, wr.grad) < 6e-3
+    assert _rel(b.grad, br.grad) < 1e-5
+    assert torch.equal(res.grad, dy)
+
+
+@pytest.mark.parametrize("kind,Cin,Cout,H", [("plain", 320, 640, 16), ("up", 640, 640, 8), ("down", 320, 320, 16)])
+def test_conv_dgrad(kind, Cin, Cout, H):
+    from adaprompt_b200.packing import pack_conv3x3
+    from adaprompt_b200.train import Conv3x3Fn, DownsampleConvFn, UpsampleConvFn, _flip_conv_pack
+    B = 2
+    w = _rand(Cout, Cin, 3, 3, seed=1) * 0.05
+    bias = _rand(Cout, seed=2)
+    wb = w.to(torch.bfloat16).float()
+    pk, pkb = pack_conv3x3(w), _flip_conv_pack(w)
+    if kind == "plain":
+        y = _rand(B, H, H, Cin, seed=3, dtype=torch.bfloat16).requires_grad_(True)
+        out = Conv3x3Fn.apply(y, pk, pkb, bias, None, None)
+        xr = y.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+        ref = F.conv2d(xr, wb, bias, padding=1)
+        leaf = y
+    else:
+        x = _rand(B, H, H, Cin, seed=3).requires_grad_(True)
+        xr = x.detach().to(torch.bfloat16).float().permute(0, 3, 1, 2).requires_grad_(True)
+        if kind == "up":
+            out = UpsampleConvFn.apply(x, pk, pkb, bias)
+            ref = F.conv2d(F.interpolate(xr, scale_factor=2, mode="nearest"), wb, bias, padding=1)
+        else:
+            out = DownsampleConvFn.apply(x, pk, pkb, bias)
+            ref = F.conv2d(xr, wb, bias, stride=2, padding=1)
+        leaf = x
+    dy = _rand(*out.shape, seed=4)
+    out.backward(dy)
+    ref.backward(dy.to(torch.bfloat16).float().permute(0, 3, 1, 2))
+    assert _rel(out, ref.permute(0, 2, 3, 1)) < 1e-4
+    assert _rel(leaf.grad, xr.grad.permute(0, 2, 3, 1)) < (6e-3 if kind == "plain" else 1e-4)
+
+
+def test_conv_out_dgrad():
+    from adaprompt_b200 import ops
+    B, H, C = 2, 16, 320
+    w = _rand(4, C, 3, 3, seed=1) * 0.05
+    dout = _rand(B, 4, H, H, seed=2)
+    xr = torch.zeros(B, C, H, H, device=DEV, requires_grad=True)
+    F.conv2d(xr, w, None, padding=1).backward(dout)
+    assert _rel(ops.conv_out_dgrad(dout, w.contiguous(), C), xr.grad.permute(0, 2, 3, 1)) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,N,nk,d", [(2, 256, 256, 40), (1, 1024, 1024, 80), (2, 64, 64, 160), (2, 512, 77, 40), (3, 256, 77, 80),
+                                      (2, 64, 77, 160)])
+def test_attention_backward(B, N, nk, d):
+    from adaprompt_b200.packing import head_pad
+    from adaprompt_b200.train import AttentionFn
+    h, dp = 8, head_pad(d)
+    nkp = (nk + 7) // 8 * 8
+    sc = d ** -0.5 * math.log2(math.e)
+    q = torch.zeros(B * N, h, dp, device=DEV)
+    q[..., :d] = _rand(B * N, h, d, seed=1) * sc
+    k = torch.zeros(B, nkp, h, dp, device=DEV)
+    k[:, :nk, :, :d] = _rand(B, nk, h, d, seed=2)
+    v = torch.zeros(B, nkp, h, d, device=DEV)
+    v[:, :nk] = _rand(B, nk, h, d, seed=3)
+    qb = q.reshape(B * N, h * dp).to(torch.bfloat16).requires_grad_(True)
+    kb = k.reshape(B * nkp, h * dp).to(torch.bfloat16).requires_grad_(True)
+    vb = v.reshape(B * nkp, h * d).to(torch.bfloat16).requires_grad_(True)
+    dO = _rand(B * N, h * d, seed=4, dtype=torch.bfloat16)
+    o = AttentionFn.apply(qb, kb, vb, B, h, d, N, nk, nkp)
+    o.backward(dO)
+    qr = qb.detach().float().reshape(B, N, h, dp).requires_grad_(True)
+    kr = kb.detach().float().reshape(B, nkp, h, dp).requires_grad_(True)
+    vr = vb.detach().float().reshape(B, nkp, h, d).requires_grad_(True)
+    s = torch.einsum("bihd,bjhd->bhij", qr, kr[:, :nk]) * math.log(2.0)
+    ref = torch.einsum("bhij,bjhd->bihd", torch.softmax(s, -1), vr[:, :nk]).reshape(B * N, h * d)
+    ref.backward(dO.float())
+    assert _rel(o, ref) < 6e-3
+    assert _rel(qb.grad.reshape(B, N, h, dp), qr.grad) < 2e-2
+    assert _rel(kb.grad.reshape(B, nkp, h, dp), kr.grad) < 2e-2
+    assert _rel(vb.grad.reshape(B, nkp, h, d), vr.grad) < 2e-2
+
+
+def test_attention_small_backward_mkv():
+    from adaprompt_b200 import ops
+    B, L, heads = 2, 77, 12
+    for mult in (1, 2):
+        ld = 768 + 2 * 768 * mult
+        qkv = _rand(B * L, ld, seed=mult, dtype=torch.bfloat16)
+        dout = _rand(B * L, 768, seed=9, dtype=torch.bfloat16)
+        dqkv = ops.attention_small_bwd(qkv, dout, B=B, heads=heads, L=L, k_off=768, v_off=768 + 768 * mult, mult=mult)
+        t = qkv.float().requires_grad_(True)
+        q = t[:, :768].reshape(B, L, heads, 64)
+        k = t[:, 768:768 + 768 * mult].reshape(B, L, heads, mult, 64)
+        v = t[:, 768 + 768 * mult:].reshape(B, L, heads, mult, 64)
+        s = torch.einsum("bihd,bjhrd->bhijr", q * 0.125, k)
+        causal = torch.ones(L, L, device=DEV).tril().bool()
+        s = s.masked_fill(~causal[None, None, :, :, None], float("-inf")).reshape(B, heads, L, L * mult)
+        p = torch.softmax(s, -1).reshape(B, heads, L, L, mult)
+        o = torch.einsum("bhijr,bjhrd->bihd", p, v).reshape(B * L, 768)
+        o.backward(dout.float())
+        fwd = torch.empty(B * L, 768, device=DEV, dtype=torch.bfloat16)
+        ops.attention_small(qkv, fwd, B=B, heads=heads, L=L, k_off=768, v_off=768 + 768 * mult, mult=mult)
+        assert _rel(fwd, o) < 6e-3
+        assert _rel(dqkv, t.grad) < 8e-3
+
+
+# ------------------------------------------------------------------------------------------------ whole UNet
+def _unet():
+    from adaprompt_b200.ldm_lite import SD15_UNET_CONFIG
+    from adaprompt_b200.unet import UNetModel
+    from adaprompt_b200.weights import spec_of, synth_state_dict
+    with torch.device("meta"):
+        unet = UNetModel(**SD15_UNET_CONFIG)
+    unet = unet.to_empty(device=DEV)
+    sd = synth_state_dict(spec_of(unet), 1234)
+    unet.load_state_dict(sd)
+    return unet.eval(), sd
+
+
+def test_unet_context_gradient_matches_oracle_autograd():
+    """d loss / d context of one distillation micro-step (batch 2, 32x32 latent) against autograd through the fp32
+    CPU oracle.  Tolerance: 5e-2 relative L2 (bf16 operands through ~60 backward layers; the reference student runs
+    TF32, main.py:815)."""
+    from adaprompt_b200.train import distill_loss, unet_forward_train
+    from oracle.golden_inputs import EXTRA_INFO
+    from oracle.unet_oracle import UNetSpec, unet_forward
+    unet, sd = _unet()
+    g = torch.Generator().manual_seed(17)
+    B = 2
+    x = torch.randn(B, 4, 32, 32, generator=g)
+    t = torch.tensor([501, 121])
+    ctx = torch.randn(16 * B, 77, 768, generator=g)
+    target = torch.randn(B, 4, 32, 32, generator=g)
+    c_ref = ctx.clone().requires_grad_(True)
+    eps_ref = unet_forward(sd, UNetSpec(), x, t, c_ref, dict(EXTRA_INFO))
+    loss_ref = F.mse_loss(eps_ref, target)
+    loss_ref.backward()
+    c = ctx.to(DEV).requires_grad_(True)
+    eps = unet_forward_train(unet, x.to(DEV), t.to(DEV), c, dict(EXTRA_INFO))
+    loss = distill_loss(eps, target.to(DEV))
+    loss.backward()
+    assert _rel(eps, eps_ref) < 1e-2
+    assert abs(loss.item() - loss_ref.item()) < 1e-2 * abs(loss_ref.item())
+    err = _rel(c.grad, c_ref.grad)
+    per_layer = [_rel(c.grad.reshape(B, 16, 77, 768)[:, l], c_ref.grad.reshape(B, 16, 77, 768)[:, l]) for l in range(16)]
+    print("context grad rel-L2", err, "per layer", [f"{e:.3f}" for e in per_layer])
+    assert err < 5e-2, (err, per_layer)
