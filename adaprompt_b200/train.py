@@ -103,7 +103,7 @@ class LinearFn(Function):
         ctx.wt = wt
         ctx.has_res = residual is not None
         ctx.x_dtype = x.dtype
-        ctx.save_for_backward(x if (w_param is not None and w_param.requires_grad) else None)
+        ctx.save_for_backward(x if ctx.needs_input_grad[6] else None)
         ctx.K = x.shape[1]
         return out
 

@@ -1,0 +1,335 @@
+"""Stage-1 distillation step, conditioning half and step driver (SURVEY.md section 8 row T1, configs[3]).
+
+Gradient path of the reference (ldm/models/diffusion/ddpm.py):
+  loss (:3010-3037) -> UNet (frozen, train.py) -> layerwise context c [16B,77,768]
+       -> FrozenCLIPEmbedder (frozen weights, ldm/modules/encoders/modules.py:260-283,361-370)
+       -> EmbeddingManager splice (embedding_manager.py:1516-1562; rows of the 16 ID tokens)
+       -> SubjBasisGenerator.forward (adaface/subj_basis_generator.py:470-567, is_training=True):
+          prompt2token_proj = a TRAINABLE CLIP text model (arc2face_models.py:178-280) + hidden_state_layer_weights
+          (grad scaler 5, :498,:580) + prompt2token_proj_grad_scaler (:528-529).
+Data parallel: one process per GPU, one all-reduce (mean) of the SubjBasisGenerator gradients per optimizer step in a
+single flat fp32 bucket over NCCL / NVLink (main.py:829 uses Lightning DDP for the same exchange).
+
+As in train.py, torch.autograd is the tape; the arithmetic of every layer is a C-ABI kernel.  Index plumbing
+(embedding-row gather / scatter, the x16 layer repeat, concatenations) uses torch tensor ops.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+from torch.autograd import Function
+
+from . import ops
+from .adaface_util import _tokenize, arc2face_forward_face_embs
+from .clip_text import CLIPEncoderLayer, CLIPTextTransformer
+from .train import LayerNormFn, distill_loss, linear, unet_forward_train
+
+N_CA_LAYERS = 16
+
+
+class GradScale(Function):
+    """adaface/util.py:28-47 ScaleGrad: identity forward, gradient times alpha."""
+
+    @staticmethod
+    def forward(ctx, x, alpha):
+        ctx.alpha = float(alpha)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.alpha, None
+
+
+def grad_scale(x, alpha):
+    """gen_gradient_scaler (adaface/util.py:60-72): alpha 1 -> identity, 0 -> detach."""
+    if alpha == 1:
+        return x
+    if alpha == 0:
+        return x.detach()
+    return GradScale.apply(x, alpha)
+
+
+class QuickGeluFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.quick_gelu(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.quick_gelu(x, dy.contiguous())
+
+
+class AttnSmallFn(Function):
+    """CLIP text self-attention (77 tokens, causal, MKV aware): qkv bf16 [B*L, E*(1+2m)] -> bf16 [B*L, E]."""
+
+    @staticmethod
+    def forward(ctx, qkv, B, heads, L, E, m, scale):
+        o = torch.empty(B * L, E, dtype=torch.bfloat16, device=qkv.device)
+        ops.attention_small(qkv, o, B=B, heads=heads, L=L, k_off=E, v_off=E + E * m, mult=m, scale=scale, causal=True)
+        ctx.save_for_backward(qkv)
+        ctx.geom = (B, heads, L, E, m, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        (qkv,) = ctx.saved_tensors
+        B, heads, L, E, m, scale = ctx.geom
+        dqkv = ops.attention_small_bwd(qkv, do.contiguous(), B=B, heads=heads, L=L, k_off=E, v_off=E + E * m, mult=m,
+                                       scale=scale, causal=True)
+        return dqkv, None, None, None, None, None, None
+
+
+class SpliceRowsFn(Function):
+    """EmbeddingManager row replacement (embedding_manager.py:1516-1562): dst[r, first[r]+k] = src[src_index[r], k].
+    dst carries no gradient of its own rows that were overwritten; src gets the gathered rows back."""
+
+    @staticmethod
+    def forward(ctx, dst, src, first, src_index):
+        out = dst.clone()
+        ops.splice_rows(out, src.contiguous(), first, src_index)
+        ctx.save_for_backward(first, src_index)
+        ctx.src_shape = src.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        first, src_index = ctx.saved_tensors
+        S, K, D = ctx.src_shape
+        rows = torch.nonzero(first >= 0).flatten()
+        cols = first[rows].long()[:, None] + torch.arange(K, device=g.device)[None]
+        picked = g[rows[:, None], cols]                                   # [R', K, D]
+        dsrc = torch.zeros(S, K, D, dtype=g.dtype, device=g.device)
+        dsrc.index_add_(0, src_index[rows].long(), picked)
+        dd = g.clone()
+        dd[rows[:, None], cols] = 0
+        return dd, dsrc, None, None
+
+
+# ------------------------------------------------------------------------------------------------ CLIP text layers
+def _kv_rows(w, m, H, hd):
+    # reference key order (arc2face_models.py:117-131) -> kernel order [head][r][hd]; same as CLIPEncoderLayer._pack
+    return w.reshape(m, H, hd, *w.shape[1:]).transpose(0, 1).reshape(m * H * hd, *w.shape[1:])
+
+
+def _bf16_pair(w: torch.Tensor):
+    wb = w.detach().to(torch.bfloat16).contiguous()
+    return wb, wb.t().contiguous()
+
+
+def _layer_weights(layer: CLIPEncoderLayer, trainable: bool) -> dict:
+    """fp32 (weight, bias) views in kernel layout + bf16 operand packs.  Trainable layers rebuild them every step (the
+    weights move); frozen layers cache them."""
+    if not trainable:
+        c = layer.__dict__.get("_train_pk")
+        if c is not None:
+            return c
+    a = layer.self_attn
+    E, H, hd = a.embed_dim, a.num_heads, a.head_dim
+    m = a.k_proj.weight.shape[0] // E
+    wqkv = torch.cat([a.q_proj.weight, _kv_rows(a.k_proj.weight, m, H, hd), _kv_rows(a.v_proj.weight, m, H, hd)], 0)
+    bqkv = torch.cat([a.q_proj.bias, _kv_rows(a.k_proj.bias, m, H, hd), _kv_rows(a.v_proj.bias, m, H, hd)], 0)
+    out = {"m": m}
+    for name, (w, b) in {"qkv": (wqkv, bqkv), "o": (a.out_proj.weight, a.out_proj.bias),
+                         "fc1": (layer.mlp.fc1.weight, layer.mlp.fc1.bias),
+                         "fc2": (layer.mlp.fc2.weight, layer.mlp.fc2.bias)}.items():
+        wb, wt = _bf16_pair(w)
+        out[name] = (wb, wt, b.detach().float().contiguous(), w if trainable else None, b if trainable else None)
+    if not trainable:
+        layer.__dict__["_train_pk"] = out
+    return out
+
+
+def _lin(x, pk, residual=None, out_dtype=torch.float32):
+    wb, wt, b, wp, bp = pk
+    return linear(x, wb, wt, b, residual=residual, out_dtype=out_dtype, w_param=wp, b_param=bp)
+
+
+def clip_layer_train(layer: CLIPEncoderLayer, h: torch.Tensor, B: int, L: int, trainable: bool) -> torch.Tensor:
+    """HF CLIPEncoderLayer as CLIPEncoderLayer._run, with grad.  h fp32 [B*L, E]."""
+    a = layer.self_attn
+    E, H = a.embed_dim, a.num_heads
+    pk = _layer_weights(layer, trainable)
+    ln1, ln2 = layer.layer_norm1, layer.layer_norm2
+    p = (lambda t: t) if trainable else (lambda t: t.detach())
+    x = LayerNormFn.apply(h, p(ln1.weight), p(ln1.bias), float(ln1.eps), torch.bfloat16)
+    qkv = _lin(x, pk["qkv"], out_dtype=torch.bfloat16)
+    o = AttnSmallFn.apply(qkv, B, H, L, E, pk["m"], a.scale)
+    h1 = _lin(o, pk["o"], residual=h)
+    x2 = LayerNormFn.apply(h1, p(ln2.weight), p(ln2.bias), float(ln2.eps), torch.bfloat16)
+    u = QuickGeluFn.apply(_lin(x2, pk["fc1"], out_dtype=torch.bfloat16))
+    return _lin(u, pk["fc2"], residual=h1)
+
+
+def clip_encode_train(tm: CLIPTextTransformer, h: torch.Tensor, layer_weights, trainable: bool) -> torch.Tensor:
+    """CLIPTextTransformer.encode with grad.  h fp32 [B, L, E] (token + position embeddings); layer_weights: None, a
+    sequence of already-normalised floats, or a tensor [n, 1] (normalised here, arc2face_models.py:236-246) that may
+    require grad.  Returns the final-LayerNormed fp32 [B, L, E]."""
+    B, L, E = h.shape
+    x = h.reshape(B * L, E).contiguous()
+    states = [x]
+    for layer in tm.encoder.layers:
+        x = clip_layer_train(layer, x, B, L, trainable)
+        states.append(x)
+    if layer_weights is None:
+        mixed = states[-1]
+    else:
+        if torch.is_tensor(layer_weights):
+            w = layer_weights.reshape(-1)
+            w = w / w.sum()
+        else:
+            w = [float(v) for v in layer_weights]
+        n = len(w)
+        mixed = sum(w[i] * states[len(states) - n + i] for i in range(n))
+    ln = tm.final_layer_norm
+    p = (lambda t: t) if trainable else (lambda t: t.detach())
+    out = LayerNormFn.apply(mixed, p(ln.weight), p(ln.bias), float(ln.eps), torch.float32)
+    return out.reshape(B, L, E)
+
+
+# ------------------------------------------------------------------------------------------------ SubjBasisGenerator
+def sbg_forward_train(sbg, arc2face_id_embs: torch.Tensor, out_id_embs_scale: float = 1.0):
+    """SubjBasisGenerator.forward(is_training=True), face branch (subj_basis_generator.py:470-567), with grad w.r.t.
+    prompt2token_proj and hidden_state_layer_weights.  -> (adaface_subj_embs [BS,L,16,768], adaface_prompt_embs)."""
+    tm = sbg.prompt2token_proj.text_model
+    dev = arc2face_id_embs.device
+    BS = arc2face_id_embs.shape[0]
+    trainable = sbg.prompt2token_proj_grad_scale != 0
+    hw = sbg.hidden_state_layer_weights
+    if hw is not None:
+        hw = grad_scale(hw, 5)                                                                      # :498,:580
+    if sbg.pad_embeddings is None:
+        sbg.generate_pad_embeddings()
+    pad_embeddings = sbg.pad_embeddings.to(dev)
+    template = ["photo of a " + ", " * 16 for _ in range(BS)]                                      # adaface/util.py:165
+    input_ids = _tokenize(sbg.clip_tokenizer, template, 77, dev)
+    emb = tm.embeddings
+    tok_w = emb.token_embedding.weight if trainable else emb.token_embedding.weight.detach()
+    pos_w = emb.position_embedding.weight if trainable else emb.position_embedding.weight.detach()
+    tok = tok_w[input_ids]                                                                          # gather (+ scatter-add backward)
+    tok = torch.cat([tok[:, :4], arc2face_id_embs.float(), tok[:, 20:]], dim=1)                     # adaface/util.py:184
+    h = tok + pos_w[None, :77]
+    with torch.set_grad_enabled(trainable and torch.is_grad_enabled()):
+        prompt_embeds = clip_encode_train(tm, h, hw, trainable)                                     # arc2face_models.py:204-248
+    core = prompt_embeds[:, 4:20]
+    full_pad = torch.cat([prompt_embeds[:, :22], pad_embeddings[22:-1].expand(BS, -1, -1), prompt_embeds[:, -1:]], 1)
+    full_pad = grad_scale(full_pad, sbg.prompt2token_proj_grad_scale)                               # :528-529
+    core = grad_scale(core, sbg.prompt2token_proj_grad_scale)
+    subj = core.unsqueeze(1).repeat(1, sbg.num_out_layers, 1, 1)                                    # :558
+    if out_id_embs_scale != 1:
+        pe = pad_embeddings[4:4 + sbg.num_out_embs_per_layer].unsqueeze(0).unsqueeze(0)
+        subj = subj * out_id_embs_scale + pe * (1 - out_id_embs_scale)
+    return subj, full_pad
+
+
+def conditioning_train(frozen_tm: CLIPTextTransformer, tokens: torch.Tensor, adaface_subj_embs: torch.Tensor,
+                       placeholder_token: int, K: int = 16, dedup: bool = True) -> torch.Tensor:
+    """EmbeddingManager.forward + FrozenCLIPEmbedder with grad w.r.t. adaface_subj_embs [BS, 16, K, 768].
+    tokens int64 [B, 77] -> c fp32 [16*B, 77, 768] (layer index minor to batch, embedding_manager.py:1349-1353).
+    dedup: encode one of the 16 layer copies when they are identical (always true for the face branch, :558)."""
+    B, N = tokens.shape
+    L = N_CA_LAYERS
+    tw = frozen_tm.embeddings.token_embedding.weight.detach().float().contiguous()
+    pos = frozen_tm.embeddings.position_embedding.weight.detach().float()
+    emb = ops.gather_rows(tw, tokens.contiguous())                                                 # [B, N, 768]
+    first_b = ops.find_first_token(tokens.contiguous(), placeholder_token)                         # [B]
+    has = first_b >= 0
+    occurs = int(has.sum().item())
+    BS = adaface_subj_embs.shape[0]
+    if occurs and BS < occurs:
+        adaface_subj_embs = adaface_subj_embs.repeat(occurs // BS, 1, 1, 1)                        # :1449-1451
+        BS = adaface_subj_embs.shape[0]
+    identical = dedup and adaface_subj_embs.shape[1] == L
+    if identical:
+        with torch.no_grad():
+            identical = bool((adaface_subj_embs == adaface_subj_embs[:, :1]).all().item())
+    w = frozen_tm.last_layers_skip_weights
+    if identical:
+        rank = (torch.cumsum(has.int(), 0) - 1).clamp_min(0).to(torch.int32)
+        src = adaface_subj_embs[:, 0, :K].contiguous()                                             # [BS, K, 768]
+        src_index = (rank % BS).contiguous()
+        spliced = SpliceRowsFn.apply(emb, src, first_b, src_index) if occurs else emb
+        z = clip_encode_train(frozen_tm, spliced + pos[None, :N], w, trainable=False)
+        return z.unsqueeze(1).expand(B, L, N, z.shape[-1]).reshape(B * L, N, z.shape[-1])
+    emb16 = emb.unsqueeze(1).repeat(1, L, 1, 1).view(B * L, N, -1)
+    first16 = first_b.repeat_interleave(L).contiguous()
+    has16 = first16 >= 0
+    rank16 = (torch.cumsum(has16.int(), 0) - 1).clamp_min(0).to(torch.int32)
+    src = adaface_subj_embs.reshape(BS * adaface_subj_embs.shape[1], *adaface_subj_embs.shape[2:])[:, :K].contiguous()
+    src_index = (rank16 % src.shape[0]).contiguous()
+    spliced = SpliceRowsFn.apply(emb16, src, first16, src_index) if occurs else emb16
+    return clip_encode_train(frozen_tm, spliced + pos[None, :N], w, trainable=False)
+
+
+# ------------------------------------------------------------------------------------------------ step driver
+def trainable_parameters(sbg) -> List[torch.nn.Parameter]:
+    return [p for p in sbg.parameters() if p.requires_grad]
+
+
+def allreduce_gradients(params: Sequence[torch.nn.Parameter], world_size: int, group=None) -> Optional[torch.Tensor]:
+    """One flat fp32 bucket, one all-reduce (SUM), scaled to the mean: the only data-path collective of the step
+    (SURVEY.md section 8(e)).  NCCL over NVLink / NVSwitch on GPUs, gloo in the CPU tests.  Returns the bucket."""
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return None
+    flat = torch.cat([g.reshape(-1).float() for g in grads])
+    if world_size > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat /= world_size
+    o = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[o:o + n].view_as(g))
+        o += n
+    return flat
+
+
+def clip_grad_norm(params: Sequence[torch.nn.Parameter], max_norm: float = 0.5) -> float:
+    """gradient_clip_val 0.5 by norm (ddpm.py:607 / Lightning trainer)."""
+    grads = [p.grad for p in params if p.grad is not None]
+    total = math.sqrt(sum(float(g.float().pow(2).sum()) for g in grads))
+    scale = max_norm / (total + 1e-6)
+    if scale < 1:
+        for g in grads:
+            g.mul_(scale)
+    return total
+
+
+class DistillStep:
+    """One Stage-1 zero-shot distillation micro-step (ddpm.py:2953-3039 with num_denoising_steps = 1):
+    x_noisy = sqrt(a_t) x0 + sqrt(1 - a_t) noise (:416-419) -> student UNet with the AdaFace prompt ->
+    MSE against the teacher's noise prediction.  The teacher (Arc2Face UNet, ddpm.py:5402-5478) is SURVEY.md
+    section 8(f) N4; its eps is an input here."""
+
+    def __init__(self, unet, frozen_tm: CLIPTextTransformer, sbg, arc2face_text_encoder, tokenizer, alphas_cumprod,
+                 placeholder_token: int, extra_info: Optional[dict] = None):
+        self.unet, self.frozen_tm, self.sbg = unet, frozen_tm, sbg
+        self.arc2face, self.tokenizer = arc2face_text_encoder, tokenizer
+        self.acp = torch.as_tensor(alphas_cumprod, dtype=torch.float32)
+        self.placeholder_token = placeholder_token
+        self.extra_info = dict(extra_info or {"use_layerwise_context": True, "use_conv_attn_kernel_size": -1,
+                                              "placeholder2indices": None, "is_training": True})
+
+    def q_sample(self, x0, t, noise):
+        a = self.acp.to(x0.device)[t].view(-1, 1, 1, 1)
+        return a.sqrt() * x0 + (1 - a).sqrt() * noise
+
+    def context(self, face_embs: torch.Tensor, tokens: torch.Tensor) -> torch.Tensor:
+        with torch.no_grad():
+            _, id_embs = arc2face_forward_face_embs(self.tokenizer, self.arc2face, face_embs)     # embedding_manager.py:1424
+        subj, _ = sbg_forward_train(self.sbg, id_embs)
+        return conditioning_train(self.frozen_tm, tokens, subj, self.placeholder_token)
+
+    def loss(self, x0, t, noise, teacher_eps, face_embs, tokens) -> torch.Tensor:
+        c = self.context(face_embs, tokens)
+        eps = unet_forward_train(self.unet, self.q_sample(x0, t, noise), t, c, dict(self.extra_info))
+        return distill_loss(eps, teacher_eps)
+
+    def micro_step(self, batch: Dict[str, torch.Tensor], accum: int = 1) -> float:
+        loss = self.loss(batch["x0"], batch["t"], batch["noise"], batch["teacher_eps"], batch["face_embs"], batch["tokens"])
+        (loss / accum).backward()
+        return float(loss.detach())

@@ -76,3 +76,35 @@ def test_wrapper_prompt_rewriting():
     assert w.update_prompt("a photo of z in a park") == f"a photo of {w.placeholder_tokens_str} in a park"
     assert w.update_prompt("a zebra") == w.placeholder_tokens_str + " a zebra"        # 'z' must be a whole word
     assert w.update_prompt(w.placeholder_tokens_str + " x") == w.placeholder_tokens_str + " x"
+
+
+# ------------------------------------------------------------------------------------------------ training all-reduce
+def _grad_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from adaprompt_b200.train_cond import allreduce_gradients, clip_grad_norm
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
+    g = torch.Generator().manual_seed(100 + rank)
+    params[0].grad = torch.randn(5, 3, generator=g)
+    params[1].grad = torch.randn(7, generator=g)          # params[2] has no gradient on any rank: skipped
+    flat = allreduce_gradients(params, world)
+    total = clip_grad_norm(params, 0.5)
+    torch.save({"g0": params[0].grad, "g1": params[1].grad, "flat": flat, "total": total}, os.path.join(out_dir, f"g{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_gradient_allreduce_is_the_mean(tmp_path):
+    """Stage-1 step: one flat bucket, all-reduce SUM / world, then clip by norm 0.5."""
+    world = 2
+    mp.spawn(_grad_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    gens = [torch.Generator().manual_seed(100 + r) for r in range(world)]
+    g0 = [torch.randn(5, 3, generator=g) for g in gens]
+    g1 = [torch.randn(7, generator=g) for g in gens]
+    m0, m1 = sum(g0) / world, sum(g1) / world
+    total = float(torch.cat([m0.reshape(-1), m1.reshape(-1)]).norm())
+    scale = min(1.0, 0.5 / (total + 1e-6))
+    for r in range(world):
+        o = torch.load(os.path.join(str(tmp_path), f"g{r}.pt"))
+        assert o["flat"].numel() == 22 and abs(o["total"] - total) < 1e-5
+        assert torch.allclose(o["g0"], m0 * scale, atol=1e-6) and torch.allclose(o["g1"], m1 * scale, atol=1e-6)

@@ -295,3 +295,136 @@ def test_unet_context_gradient_matches_oracle_autograd():
     per_layer = [_rel(c.grad.reshape(B, 16, 77, 768)[:, l], c_ref.grad.reshape(B, 16, 77, 768)[:, l]) for l in range(16)]
     print("context grad rel-L2", err, "per layer", [f"{e:.3f}" for e in per_layer])
     assert err < 5e-2, (err, per_layer)
+
+
+# ------------------------------------------------------------------------------------------------ conditioning half
+def _clip_small(seed, layers, kv_mult=None):
+    from adaprompt_b200.clip_text import CLIPTextConfigLite, CLIPTextModelWrapper
+    from oracle import text_oracle as to
+    sd = to.clip_synth_state_dict(seed, num_layers=layers, kv_mult=kv_mult)
+    m = CLIPTextModelWrapper(CLIPTextConfigLite(num_hidden_layers=layers))
+    if kv_mult:
+        m.extend_clip_attention_MKV_multiplier(-1, -1, kv_mult[0], noise_std=0)
+    m.load_state_dict(sd)
+    return m.cuda(), sd
+
+
+def _sbg_small(seed, layers, kv_mult=None, grad_scale=1.0):
+    from adaprompt_b200.subj_basis_generator import SubjBasisGenerator
+    from test_text_gpu import StubTokenizer
+    m, sd = _clip_small(seed, layers, kv_mult)
+    s = SubjBasisGenerator(num_out_embs_per_layer=16, clip_tokenizer=StubTokenizer(), prompt2token_proj_grad_scale=grad_scale)
+    s.prompt2token_proj = m
+    return s.cuda().train(), sd
+
+
+def _cond_reference(sd_sbg, sd_frozen, hw, id_embs, tokens):
+    from oracle import text_oracle as to
+    subj, _ = to.subj_basis_generator_forward(sd_sbg, id_embs, hw, is_training=True)
+    embedded = sd_frozen["text_model.embeddings.token_embedding.weight"][tokens]
+    static, _, _ = to.splice_subject_embeddings(tokens, embedded, subj)
+    return to.frozen_clip_encode(sd_frozen, tokens, static)
+
+
+def _compare_param_grads(module, sd_ref, prefix="", tol=5e-2, skip=()):
+    worst = ("", 0.0)
+    for name, p in module.named_parameters():
+        ref = sd_ref[prefix + name].grad
+        if name in skip or name.endswith("k_proj.bias"):
+            continue   # softmax is invariant to a key bias (q.b is constant along a row): its true gradient is 0
+        if ref is None or ref.abs().max() == 0:
+            assert p.grad is None or p.grad.abs().max() == 0, name
+            continue
+        assert p.grad is not None, name
+        e = _rel(p.grad, ref)
+        if e > worst[1]:
+            worst = (name, e)
+        assert e < tol, (name, e)
+    return worst
+
+
+@pytest.mark.parametrize("kv_mult", [None, {0: 2, 1: 2, 2: 2}])
+def test_conditioning_gradients_match_oracle_autograd(kv_mult):
+    """SubjBasisGenerator (trainable CLIP text layers, MKV aware) -> splice -> frozen CLIP: every parameter gradient
+    against autograd through the CPU oracle chain.  Tolerance 5e-2 relative L2 per parameter tensor."""
+    from adaprompt_b200.train_cond import conditioning_train, sbg_forward_train
+    from oracle import text_oracle as to
+    sbg, sd_sbg = _sbg_small(21, 3, kv_mult)
+    frozen, sd_frozen = _clip_small(22, 3)
+    frozen.text_model.last_layers_skip_weights = [0.5, 0.5]
+    for p in frozen.parameters():
+        p.requires_grad = False
+    g = torch.Generator().manual_seed(5)
+    id_embs = torch.randn(2, 16, 768, generator=g) * 0.05
+    tokens = torch.tensor([to.subject_prompt_ids(77), to.pad_ids([to.TOK_A, to.TOK_PHOTO]), to.subject_prompt_ids(77)])
+    R = torch.randn(48, 77, 768, generator=g)
+    # ---- reference
+    sd_ref = {k: v.clone().requires_grad_(True) for k, v in sd_sbg.items()}
+    hw_ref = torch.tensor([[1.0], [2.0], [4.0]], requires_grad=True)
+    c_ref = _cond_reference(sd_ref, sd_frozen, hw_ref, id_embs, tokens)
+    (c_ref * R).sum().backward()
+    # ---- B200 path
+    subj, _ = sbg_forward_train(sbg, id_embs.cuda())
+    c = conditioning_train(frozen.text_model, tokens.cuda(), subj, to.TOK_Z)
+    assert _rel(c, c_ref) < 1e-2
+    (c * R.cuda()).sum().backward()
+    worst = _compare_param_grads(sbg.prompt2token_proj, sd_ref, skip=("text_model.embeddings.token_embedding.weight",))
+    tok_g = sbg.prompt2token_proj.text_model.embeddings.token_embedding.weight.grad
+    tok_ref = sd_ref["text_model.embeddings.token_embedding.weight"].grad
+    rows = tok_ref.abs().sum(1).nonzero().flatten()
+    assert _rel(tok_g[rows.cuda()], tok_ref[rows]) < 5e-2 and float(tok_g.abs().sum()) > 0
+    e_hw = _rel(sbg.hidden_state_layer_weights.grad, 5 * hw_ref.grad)       # grad scaler 5 (subj_basis_generator.py:580)
+    print("worst parameter", worst, "hidden_state_layer_weights", e_hw)
+    assert e_hw < 5e-2
+    assert all(p.grad is None for p in frozen.parameters())
+
+
+def test_distill_step_end_to_end_gradients():
+    """Whole micro-step (configs[3] geometry scaled down: batch 2, 32x32 latent, 2-layer CLIPs): id embeddings ->
+    SubjBasisGenerator -> splice -> frozen CLIP -> UNet -> MSE vs teacher eps; SubjBasisGenerator gradients against
+    autograd through the CPU oracle chain (conditioning oracle + UNet oracle)."""
+    from adaprompt_b200.train_cond import DistillStep, trainable_parameters
+    from oracle import text_oracle as to
+    from oracle.golden_inputs import EXTRA_INFO
+    from oracle.unet_oracle import UNetSpec, make_alphas_cumprod, unet_forward
+    from test_text_gpu import StubTokenizer
+    unet, sd_unet = _unet()
+    sbg, sd_sbg = _sbg_small(31, 2)
+    frozen, sd_frozen = _clip_small(32, 2)
+    arc2face, sd_arc = _clip_small(33, 2)
+    frozen.text_model.last_layers_skip_weights = [0.5, 0.5]
+    for m in (frozen, arc2face):
+        for p in m.parameters():
+            p.requires_grad = False
+    acp = torch.tensor(make_alphas_cumprod(), dtype=torch.float32)
+    step = DistillStep(unet, frozen.text_model, sbg, arc2face.eval(), StubTokenizer(), acp, to.TOK_Z)
+    g = torch.Generator().manual_seed(9)
+    B = 2
+    batch = {"x0": torch.randn(B, 4, 32, 32, generator=g), "noise": torch.randn(B, 4, 32, 32, generator=g),
+             "t": torch.tensor([601, 141]), "teacher_eps": torch.randn(B, 4, 32, 32, generator=g),
+             "face_embs": F.normalize(torch.randn(B, 512, generator=g), dim=-1),
+             "tokens": torch.tensor([to.subject_prompt_ids(77)] * B)}
+    # ---- reference
+    sd_ref = {k: v.clone().requires_grad_(True) for k, v in sd_sbg.items()}
+    hw_ref = torch.tensor([[1.0], [2.0], [4.0]], requires_grad=True)
+    with torch.no_grad():
+        _, id_embs = to.arc2face_forward_face_embs(sd_arc, batch["face_embs"])
+    c_ref = _cond_reference(sd_ref, sd_frozen, hw_ref, id_embs, batch["tokens"])
+    a = acp[batch["t"]].view(-1, 1, 1, 1)
+    x_noisy = a.sqrt() * batch["x0"] + (1 - a).sqrt() * batch["noise"]
+    eps_ref = unet_forward(sd_unet, UNetSpec(), x_noisy, batch["t"], c_ref, dict(EXTRA_INFO))
+    loss_ref = F.mse_loss(eps_ref, batch["teacher_eps"])
+    loss_ref.backward()
+    # ---- B200 path
+    loss = step.micro_step({k: v.cuda() for k, v in batch.items()})
+    assert abs(loss - loss_ref.item()) < 1e-2 * abs(loss_ref.item())
+    scale = sbg.prompt2token_proj_grad_scale
+    worst = ("", 0.0)
+    for name, p in sbg.prompt2token_proj.named_parameters():
+        ref = sd_ref[name].grad
+        if name.endswith("token_embedding.weight") or name.endswith("k_proj.bias") or ref is None or ref.abs().max() == 0:
+            continue
+        e = _rel(p.grad / scale, ref)
+        worst = max(worst, (name, e), key=lambda t: t[1])
+    print("end-to-end worst parameter gradient error", worst, "n trainable", len(trainable_parameters(sbg)))
+    assert worst[1] < 8e-2, worst
