@@ -108,6 +108,9 @@ SIGNATURES = {
     "af_sumpool2x2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "af_zero_insert2x": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "af_transpose_to_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_void_p, c_void_p]),
+    "af_prodigy_moments": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float,
+                                   c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p]),
+    "af_prodigy_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_void_p]),
 }
 
 _lib = None
@@ -149,7 +152,7 @@ KERNELS_PER_CALL = {
     "af_upsample2x_cast": 1, "af_cfg_ddim_update": 1, "af_advance_step": 1,
     "af_attention_bf16_lse": 1, "af_bgemm_bf16": 1, "af_groupnorm_bwd": 3, "af_layernorm_bwd": 1, "af_geglu_fwd": 1,
     "af_geglu_bwd": 1, "af_quick_gelu": 1, "af_rowdot_heads": 1, "af_attention_small_bwd": 1, "af_conv_out_dgrad": 1,
-    "af_sumpool2x2": 1, "af_zero_insert2x": 1, "af_transpose_to_bf16": 1,
+    "af_sumpool2x2": 1, "af_zero_insert2x": 1, "af_transpose_to_bf16": 1, "af_prodigy_moments": 1, "af_prodigy_apply": 1,
 }
 
 

@@ -389,6 +389,59 @@ __global__ void __launch_bounds__(256) transpose_to_bf16_kernel(const T* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------- Prodigy (ldm/prodigy.py)
+// pass 1 (:177-189): Adam moments scaled by d, s <- beta3 s + s_alpha g, and the two global sums of the d estimate:
+// sums[0] += g . (p0 - p), sums[1] += |s_new|  (double accumulators).
+__global__ void __launch_bounds__(256) prodigy_moments_kernel(const float* __restrict__ p, const float* __restrict__ grad,
+                                                              const float* __restrict__ p0, float* __restrict__ s,
+                                                              float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
+                                                              long long n, float beta1, float beta2, float beta3, float d,
+                                                              float s_alpha, float coupled_decay, double* __restrict__ sums) {
+  double dot = 0.0, den = 0.0;
+  const float c1 = d * (1.0f - beta1), c2 = d * d * (1.0f - beta2);
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
+    const float pv = p[i];
+    const float g = grad[i] + coupled_decay * pv;
+    dot += static_cast<double>(g) * static_cast<double>(p0[i] - pv);
+    exp_avg[i] = exp_avg[i] * beta1 + c1 * g;
+    exp_avg_sq[i] = exp_avg_sq[i] * beta2 + c2 * g * g;
+    const float sn = s[i] * beta3 + s_alpha * g;
+    s[i] = sn;
+    den += fabs(static_cast<double>(sn));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    den += __shfl_xor_sync(0xffffffffu, den, o);
+  }
+  __shared__ double sh[2][8];
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = dot;
+    sh[1][threadIdx.x >> 5] = den;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      a += sh[0][w];
+      b += sh[1][w];
+    }
+    atomicAdd(sums, a);
+    atomicAdd(sums + 1, b);
+  }
+}
+// pass 2 (:240-248): decoupled decay, then p -= dlr * exp_avg / (sqrt(exp_avg_sq) + d * eps)
+__global__ void __launch_bounds__(256) prodigy_apply_kernel(float* __restrict__ p, const float* __restrict__ exp_avg,
+                                                            const float* __restrict__ exp_avg_sq, long long n, float dlr,
+                                                            float d_eps, float decoupled_decay) {
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
+    float pv = p[i];
+    pv += pv * (-decoupled_decay * dlr);
+    pv += -dlr * (exp_avg[i] / (sqrtf(exp_avg_sq[i]) + d_eps));
+    p[i] = pv;
+  }
+}
+
 static inline unsigned grid_for(size_t n) {
   size_t g = (n + 255) / 256;
   const size_t cap = static_cast<size_t>(num_sms()) * 16;
@@ -531,5 +584,23 @@ extern "C" int af_transpose_to_bf16(const void* in, int in_dtype, int R, int C, 
     transpose_to_bf16_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), R, C, ldo,
                                                                      static_cast<__nv_bfloat16*>(out_bf16));
   AF_LAUNCH_CHECK("transpose_to_bf16_kernel");
+  return 0;
+}
+
+extern "C" int af_prodigy_moments(const float* p, const float* grad, const float* p0, float* s, float* exp_avg,
+                                  float* exp_avg_sq, long long n, float beta1, float beta2, float beta3, float d,
+                                  float s_alpha, float coupled_decay, double* sums, cudaStream_t stream) {
+  AF_CHECK_ARG(p && grad && p0 && s && exp_avg && exp_avg_sq && sums && n > 0, "af_prodigy_moments: bad arguments");
+  prodigy_moments_kernel<<<grid_for(static_cast<size_t>(n)), 256, 0, stream>>>(p, grad, p0, s, exp_avg, exp_avg_sq, n, beta1,
+                                                                               beta2, beta3, d, s_alpha, coupled_decay, sums);
+  AF_LAUNCH_CHECK("prodigy_moments_kernel");
+  return 0;
+}
+extern "C" int af_prodigy_apply(float* p, const float* exp_avg, const float* exp_avg_sq, long long n, float dlr, float d_eps,
+                                float decoupled_decay, cudaStream_t stream) {
+  AF_CHECK_ARG(p && exp_avg && exp_avg_sq && n > 0, "af_prodigy_apply: bad arguments");
+  prodigy_apply_kernel<<<grid_for(static_cast<size_t>(n)), 256, 0, stream>>>(p, exp_avg, exp_avg_sq, n, dlr, d_eps,
+                                                                             decoupled_decay);
+  AF_LAUNCH_CHECK("prodigy_apply_kernel");
   return 0;
 }

@@ -162,6 +162,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- model: random-init SD-1.5 architecture, same recipe as the parity tests ---------------------

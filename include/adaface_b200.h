@@ -228,6 +228,16 @@ int af_zero_insert2x(const float* in, int B, int H, int W, int C, void* out_bf16
 /* out bf16 [C][ldo] = in[R][C]^T (in fp32 or bf16), zero padded to ldo columns: weight-gradient GEMM operands. */
 int af_transpose_to_bf16(const void* in, int in_dtype, int R, int C, long long ldo, void* out_bf16, af_stream_t stream);
 
+/* Prodigy optimizer step over one flat fp32 parameter bucket (ldm/prodigy.py:97-256; the trainer's optimizer,
+ * ddpm.py configure_optimizers).  Pass 1 updates exp_avg / exp_avg_sq / s (:182-188) and ADDS g.(p0-p) and sum|s| into
+ * sums[0..1] (double; :179,:189 - the caller zeroes them and derives d, :212-216); pass 2 applies the decoupled weight
+ * decay and the Adam-style update (:240-248) with the new d. */
+int af_prodigy_moments(const float* p, const float* grad, const float* p0, float* s, float* exp_avg, float* exp_avg_sq,
+                       long long n, float beta1, float beta2, float beta3, float d, float s_alpha, float coupled_decay,
+                       double* sums, af_stream_t stream);
+int af_prodigy_apply(float* p, const float* exp_avg, const float* exp_avg_sq, long long n, float dlr, float d_eps,
+                     float decoupled_decay, af_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

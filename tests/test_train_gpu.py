@@ -428,3 +428,22 @@ def test_distill_step_end_to_end_gradients():
         worst = max(worst, (name, e), key=lambda t: t[1])
     print("end-to-end worst parameter gradient error", worst, "n trainable", len(trainable_parameters(sbg)))
     assert worst[1] < 8e-2, worst
+
+
+# ------------------------------------------------------------------------------------------------ optimizer
+@pytest.mark.parametrize("case", ["default", "decay_biascorr", "coupled_decay_growth"])
+def test_prodigy_matches_reference_golden(case):
+    """Fused flat-bucket Prodigy vs tests/golden/prodigy.pt (the UNMODIFIED ldm/prodigy.py run by
+    oracle/make_golden_prodigy.py): 12 steps on a noisy quadratic, parameters and the adapted d."""
+    import os
+    from adaprompt_b200.prodigy import Prodigy
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "prodigy.pt"))[case]
+    params = [torch.nn.Parameter(t.clone().cuda()) for t in g["init"]]
+    opt = Prodigy(params, lr=1.0, **g["kw"])
+    for step, ns in enumerate(g["noises"]):
+        for p, t, n in zip(params, g["targets"], ns):
+            p.grad = (p.detach() - t.cuda()) + n.cuda()
+        opt.step()
+        assert abs(opt.param_groups[0]["d"] - g["d"][step]) <= 2e-4 * abs(g["d"][step]), (step, opt.param_groups[0]["d"], g["d"][step])
+    for p, ref in zip(params, g["final"]):
+        assert _rel(p, ref) < 1e-4
