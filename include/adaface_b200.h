@@ -73,6 +73,17 @@ int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* A1, long lo
  * Results are bit-identical between the modes (same accumulation order). */
 int af_gemm_set_pair_mode(int mode);
 
+/* Schedule of the two-query-tile self-attention kernel (head dims 40 / 80, Nq >= 256), for A/B measurements:
+ * bit 0 = hand P to the PV MMA per 64-key piece instead of per key block, bit 1 = pass P through tensor memory
+ * (A-operand-in-TMEM MMA) instead of shared memory, bit 2 = the two softmax warps of an SM sub-partition take turns
+ * in the ex2 phase (ping-pong).  variant < 0 only queries.  Returns the previous variant. */
+int af_attention_set_pair_variant(int variant);
+/* Timeline probe of the same kernel: when device_buffer (>= 4*64*8 int64, caller-owned) is non-null, CTA (0,0,0) of every
+ * following launch records clock64 stamps: [actor: softmax warp of tile 0, of tile 1, MMA issuer 0, 1][key block < 64][8 events]
+ * (softmax: loop top, S ready, S in registers, max done, {P piece free, P piece handed over} x pieces; MMA: S issue
+ * begin / end, {PV piece begin / end}).  Null switches it off.  Measurement aid only - results are unaffected. */
+int af_attention_set_trace(long long* device_buffer);
+
 /* 3x3 convolution, pad 1, stride 1 or 2, NHWC bf16 input(s) [B,H,W,C0] (+ [B,H,W,C1] concat), weights
  * Wt[Cout][ky][kx][C0+C1] bf16, as an implicit GEMM (no im2col buffer).  Output rows are output pixels
  * (n, oh, ow) row-major.  Replaces nn.Conv2d 3x3 at openaimodel.py:155 (stride 2), :208, :234, :120-122. */
