@@ -413,6 +413,128 @@ extern "C" int af_linear_small(const float* x, const float* w, const float* bias
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row softmax of materialised attention scores (VAE AttnBlock, ldm/modules/diffusionmodules/model.py:188-193:
+// w_ = softmax(q.k * c^-1/2, dim=2)): fp32 scores [rows][n] -> bf16 probabilities [rows][ldo], one CTA per row,
+// the row lives in registers (n <= 256 threads x 16 x 4 = 16384), exp2 domain.
+// ---------------------------------------------------------------------------------------------
+namespace af {
+template <int ITER>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, long long ldx, int n,
+                                                           float scale_log2e, __nv_bfloat16* __restrict__ y,
+                                                           long long ldo) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(blockIdx.x) * ldx);
+  const int nv = n >> 2;
+  float4 v[ITER];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int k = threadIdx.x + i * 256;
+    if (k < nv) {
+      v[i] = __ldg(xr + k);
+      mx = fmaxf(mx, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    bc = m;
+  }
+  __syncthreads();
+  const float m = bc * scale_log2e;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int k = threadIdx.x + i * 256;
+    if (k < nv) {
+      v[i].x = fast_exp2(fmaf(v[i].x, scale_log2e, -m));
+      v[i].y = fast_exp2(fmaf(v[i].y, scale_log2e, -m));
+      v[i].z = fast_exp2(fmaf(v[i].z, scale_log2e, -m));
+      v[i].w = fast_exp2(fmaf(v[i].w, scale_log2e, -m));
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  s = warp_sum(s);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    bc = 1.0f / t;
+  }
+  __syncthreads();
+  const float inv = bc;
+  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(blockIdx.x) * ldo);
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int k = threadIdx.x + i * 256;
+    if (k < nv) {
+      uint2 pk;
+      pk.x = pack_bf16x2(v[i].x * inv, v[i].y * inv);
+      pk.y = pack_bf16x2(v[i].z * inv, v[i].w * inv);
+      yr[k] = pk;
+    }
+  }
+}
+}  // namespace af
+
+extern "C" int af_softmax_rows(const float* x, long long ldx, long long rows, int n, float scale, void* y_bf16,
+                               long long ldo, cudaStream_t stream) {
+  AF_CHECK_ARG(x && y_bf16 && rows > 0 && rows < (1ll << 31), "af_softmax_rows: bad args");
+  AF_CHECK_ARG(n > 0 && n % 4 == 0 && n <= 16384 && ldx % 4 == 0 && ldo % 4 == 0 && ldx >= n && ldo >= n,
+               "af_softmax_rows: n=%d ldx=%lld ldo=%lld (n%%4, n<=16384)", n, ldx, ldo);
+  if (n <= 4096)
+    softmax_rows_kernel<4><<<static_cast<unsigned>(rows), 256, 0, stream>>>(x, ldx, n, scale * 1.4426950408889634f,
+                                                                           static_cast<__nv_bfloat16*>(y_bf16), ldo);
+  else
+    softmax_rows_kernel<16><<<static_cast<unsigned>(rows), 256, 0, stream>>>(x, ldx, n, scale * 1.4426950408889634f,
+                                                                            static_cast<__nv_bfloat16*>(y_bf16), ldo);
+  AF_LAUNCH_CHECK("softmax_rows_kernel");
+  return 0;
+}
+
+// 1x1 convolution over at most 4 channels of an NCHW fp32 tensor, with an input scale: the VAE's post_quant_conv applied
+// to z / scale_factor (ldm/models/autoencoder.py:331, ldm/models/diffusion/ddpm.py:1267).
+namespace af {
+__global__ void __launch_bounds__(256) channel_mix4_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float in_scale, int Cin,
+                                                           int Cout, long long HW, long long total,
+                                                           float* __restrict__ y) {
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * 256) {
+    const long long b = i / HW, pix = i - b * HW;
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = c < Cin ? x[(b * Cin + c) * HW + pix] * in_scale : 0.f;
+    for (int o = 0; o < Cout; ++o) {
+      float acc = bias ? bias[o] : 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < Cin) acc = fmaf(w[o * Cin + c], v[c], acc);
+      y[(b * Cout + o) * HW + pix] = acc;
+    }
+  }
+}
+}  // namespace af
+
+extern "C" int af_channel_mix4(const float* x_nchw, const float* w, const float* bias, float in_scale, int B, int Cin,
+                               int Cout, long long HW, float* y_nchw, cudaStream_t stream) {
+  AF_CHECK_ARG(x_nchw && w && y_nchw && B > 0 && HW > 0, "af_channel_mix4: bad args");
+  AF_CHECK_ARG(Cin >= 1 && Cin <= 4 && Cout >= 1 && Cout <= 4, "af_channel_mix4: Cin=%d Cout=%d (1..4)", Cin, Cout);
+  const long long total = static_cast<long long>(B) * HW;
+  channel_mix4_kernel<<<grid_for(static_cast<size_t>(total), 256), 256, 0, stream>>>(x_nchw, w, bias, in_scale, Cin, Cout,
+                                                                                     HW, total, y_nchw);
+  AF_LAUNCH_CHECK("channel_mix4_kernel");
+  return 0;
+}
+
 extern "C" int af_cast_bf16(const float* x, void* y_bf16, long long n, cudaStream_t stream) {
   AF_CHECK_ARG(x && y_bf16 && n > 0 && n % 4 == 0, "af_cast_bf16: bad args (n%%4)");
   const size_t n4 = static_cast<size_t>(n) / 4;

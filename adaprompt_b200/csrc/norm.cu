@@ -85,49 +85,73 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
   }
 }
 
-// grid = (32 groups, B); block = 128.  mean_rstd[b][g] = (mean, rstd) over the group's channels of [x0 | x1].
-__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ st0, int C0, int slots0,
+// grid = (32 groups, B); block = 256.  mean_rstd[b][g] = (mean, rstd) over the group's channels of [x0 | x1].
+// Latency-bound: every thread keeps four independent 8-byte loads in flight and the block reduces with warp shuffles
+// (fixed order: bit-reproducible).
+__device__ __forceinline__ void gn_fold_source(const float2* __restrict__ base, int Cs, int lo, int w, int slots,
+                                               float& s, float& ss) {
+  const int n = w * slots;
+  const float2* col = base + lo;
+  int i = threadIdx.x;
+  for (; i + 3 * 256 < n; i += 4 * 256) {
+    int sl[4], c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      sl[u] = (i + u * 256) / w;
+      c[u] = (i + u * 256) - sl[u] * w;
+    }
+    float2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(col + static_cast<size_t>(sl[u]) * Cs + c[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s += v[u].x;
+      ss += v[u].y;
+    }
+  }
+  for (; i < n; i += 256) {
+    const int sl = i / w, c = i - sl * w;
+    const float2 v = __ldg(col + static_cast<size_t>(sl) * Cs + c);
+    s += v.x;
+    ss += v.y;
+  }
+}
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ st0, int C0, int slots0,
                                                           const float* __restrict__ st1, int C1, int slots1, int HW,
                                                           float eps, float* __restrict__ mean_rstd) {
-  __shared__ float red[2][128];
+  __shared__ float red[2][8];
   const int C = C0 + C1;
   const int cpg = C / kGroups;
   const int g = blockIdx.x, b = blockIdx.y;
   const int c_lo = g * cpg, c_hi = c_lo + cpg;
   float s = 0.f, ss = 0.f;
-  // source 0 part of the group
   {
-    const int lo = min(c_lo, C0), hi = min(c_hi, C0), w = hi - lo;
-    const float2* base = reinterpret_cast<const float2*>(st0) + static_cast<size_t>(b) * slots0 * C0;
-    for (int i = threadIdx.x; i < w * slots0; i += 128) {
-      const int sl = i / w, c = lo + (i - sl * w);
-      const float2 v = __ldg(base + static_cast<size_t>(sl) * C0 + c);
-      s += v.x; ss += v.y;
-    }
+    const int lo = min(c_lo, C0), hi = min(c_hi, C0);
+    if (hi > lo)
+      gn_fold_source(reinterpret_cast<const float2*>(st0) + static_cast<size_t>(b) * slots0 * C0, C0, lo, hi - lo, slots0, s, ss);
   }
   if (C1 > 0) {
-    const int lo = max(c_lo, C0) - C0, hi = max(c_hi, C0) - C0, w = hi - lo;
-    const float2* base = reinterpret_cast<const float2*>(st1) + static_cast<size_t>(b) * slots1 * C1;
-    for (int i = threadIdx.x; i < w * slots1; i += 128) {
-      const int sl = i / w, c = lo + (i - sl * w);
-      const float2 v = __ldg(base + static_cast<size_t>(sl) * C1 + c);
-      s += v.x; ss += v.y;
-    }
+    const int lo = max(c_lo, C0) - C0, hi = max(c_hi, C0) - C0;
+    if (hi > lo)
+      gn_fold_source(reinterpret_cast<const float2*>(st1) + static_cast<size_t>(b) * slots1 * C1, C1, lo, hi - lo, slots1, s, ss);
   }
-  red[0][threadIdx.x] = s;
-  red[1][threadIdx.x] = ss;
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s;
+    red[1][threadIdx.x >> 5] = ss;
+  }
   __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {   // fixed-shape tree: deterministic
-    if (threadIdx.x < o) {
-      red[0][threadIdx.x] += red[0][threadIdx.x + o];
-      red[1][threadIdx.x] += red[1][threadIdx.x + o];
-    }
-    __syncthreads();
-  }
   if (threadIdx.x == 0) {
+    float ts = 0.f, tss = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      ts += red[0][w];
+      tss += red[1][w];
+    }
     const float n = static_cast<float>(HW) * cpg;
-    const float mean = red[0][0] / n;
-    const float var = fmaxf(red[1][0] / n - mean * mean, 0.f);
+    const float mean = ts / n;
+    const float var = fmaxf(tss / n - mean * mean, 0.f);
     mean_rstd[(static_cast<size_t>(b) * kGroups + g) * 2] = mean;
     mean_rstd[(static_cast<size_t>(b) * kGroups + g) * 2 + 1] = rsqrtf(var + eps);
   }
@@ -305,7 +329,7 @@ extern "C" int af_groupnorm_finalize(const float* stats0, int C0, int slots0, co
   AF_CHECK_ARG(stats0 && mean_rstd, "af_groupnorm_finalize: null pointer");
   AF_CHECK_ARG(B > 0 && HW > 0 && C0 > 0 && C1 >= 0 && (C0 + C1) % 32 == 0 && slots0 > 0, "af_groupnorm_finalize: bad sizes");
   AF_CHECK_ARG(C1 == 0 || (stats1 && slots1 > 0), "af_groupnorm_finalize: second source needs stats");
-  gn_finalize_kernel<<<dim3(kGroups, B), 128, 0, stream>>>(stats0, C0, slots0, stats1, C1, slots1, HW, eps, mean_rstd);
+  gn_finalize_kernel<<<dim3(kGroups, B), 256, 0, stream>>>(stats0, C0, slots0, stats1, C1, slots1, HW, eps, mean_rstd);
   AF_LAUNCH_CHECK("gn_finalize_kernel");
   return 0;
 }

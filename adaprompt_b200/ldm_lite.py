@@ -39,11 +39,12 @@ class LatentDiffusionLite(nn.Module):
 
     def __init__(self, unet: nn.Module = None, timesteps=1000, linear_start=0.00085, linear_end=0.012,
                  beta_schedule="linear", scale_factor=0.18215, parameterization="eps", cond_stage_model=None,
-                 embedding_manager=None):
+                 embedding_manager=None, first_stage_model=None):
         super().__init__()
         self.model = DiffusionWrapper(unet if unet is not None else UNetModel(**SD15_UNET_CONFIG))
         self.cond_stage_model = cond_stage_model      # clip_text.FrozenCLIPEmbedder (ddpm.py:756)
         self.embedding_manager = embedding_manager    # embedding_manager.EmbeddingManagerLite (ddpm.py:793)
+        self.first_stage_model = first_stage_model    # vae.AutoencoderKL, decode side (ddpm.py:744-751)
         self.use_layerwise_embedding = True           # v1-inference-ada.yaml:19
         self.N_CA_LAYERS = 16                         # ddpm.py:150
         self.empty_context = None
@@ -109,6 +110,16 @@ class LatentDiffusionLite(nn.Module):
             "capture_distill_attn": False,
         }
         return (static_prompt_embedding, cond_in, extra_info)                                       # :1078
+
+    @torch.no_grad()
+    def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False, max_batch=None):
+        """ddpm.py:1260-1318, the plain branch (no VQ codebook, no split_input_params): latents -> RGB in [-1, 1]."""
+        if predict_cids or hasattr(self, "split_input_params"):
+            raise NotImplementedError("decode_first_stage: VQ / patch-split decoding is not used by AdaFace sampling")
+        if self.first_stage_model is None:
+            raise RuntimeError("LatentDiffusionLite: first_stage_model is not set")
+        from .vae import decode_first_stage
+        return decode_first_stage(self.first_stage_model, z, self.scale_factor, max_batch=max_batch)
 
     def refresh_conditioning(self, cond, batch: int):
         """Hook for the CUDA-graph sampler: (re)project the conditioning tuple's context through the 16

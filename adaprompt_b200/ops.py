@@ -318,6 +318,34 @@ def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
     return out
 
 
+def channel_mix4(x_nchw: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], in_scale: float = 1.0) -> torch.Tensor:
+    """1x1 conv over <= 4 channels of an NCHW fp32 tensor with an input scale (VAE post_quant_conv on z / scale_factor)."""
+    lib = _lib.load()
+    _chk(x_nchw, torch.float32, "x")
+    _chk(w, torch.float32, "w")
+    B, Cin, H, W = (int(s) for s in x_nchw.shape)
+    Cout = int(w.shape[0])
+    out = torch.empty(B, Cout, H, W, dtype=torch.float32, device=x_nchw.device)
+    rc = lib.af_channel_mix4(x_nchw.data_ptr(), w.data_ptr(), _p(bias), float(in_scale), B, Cin, Cout, H * W,
+                             out.data_ptr(), _stream())
+    _lib.check(rc, "af_channel_mix4")
+    return out
+
+
+def softmax_rows(x: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r] = softmax(scale * x[r]) per row: fp32 [rows, n] -> bf16 [rows, n] (VAE AttnBlock, model.py:188-193)."""
+    lib = _lib.load()
+    _chk(x, torch.float32, "x")
+    rows, n = (int(s) for s in x.shape)
+    if out is None:
+        out = torch.empty(rows, n, dtype=torch.bfloat16, device=x.device)
+    _chk(out, torch.bfloat16, "out")
+    rc = lib.af_softmax_rows(x.data_ptr(), int(x.stride(0)), rows, n, float(scale), out.data_ptr(), int(out.stride(0)),
+                             _stream())
+    _lib.check(rc, "af_softmax_rows")
+    return out
+
+
 def upsample2x_cast(x_nhwc: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     _chk(x_nhwc, torch.float32, "x")

@@ -28,6 +28,7 @@ DDIM_STEPS = 50
 IMAGES_PER_GPU = 8
 GUIDANCE = (4.0, 1.0)
 LATENT = 64
+VAE_GFLOP_PER_IMAGE = 2514.5    # first-stage decoder at 64x64 latents -> 512x512 (convs + the 4096-token AttnBlock)
 UNET_GFLOP_PER_SAMPLE = 803.27  # conv 443.95 + linear 233.27 + attention 126.05
 
 
@@ -141,6 +142,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-vae", action="store_true", help="skip the sampling + first-stage-decoder leg (vae_decode key)")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel-class table to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -249,6 +251,37 @@ def main():
     h2d = sum(t.numel() * t.element_size() for t in host.values())
     d2h = out_host.numel() * out_host.element_size()
 
+    # ---- row N1: the same call followed by the first-stage decoder (latents -> 512x512 RGB) -----
+    vae_info = None
+    if not args.no_vae:
+        from adaprompt_b200.vae import AutoencoderKL
+        with torch.device("meta"):
+            vae = AutoencoderKL()
+        vae = vae.to_empty(device=dev)
+        vae.load_state_dict(synth_state_dict(spec_of(vae), 4321))
+        vae.eval()
+        model.first_stage_model = vae
+        rgb_host = torch.empty(b, 3, 8 * LATENT, 8 * LATENT).pin_memory()
+        lat = one_call(*dev_in)
+        for _ in range(2):
+            model.decode_first_stage(lat)
+        ms_dec = timed(lambda: model.decode_first_stage(lat), args.steps) / args.steps
+
+        def step_e2e_rgb():
+            c = host["c"].to(dev, non_blocking=True)
+            uc = host["uc"].to(dev, non_blocking=True)
+            x_T = host["x_T"].to(dev, non_blocking=True)
+            rgb_host.copy_(model.decode_first_stage(one_call(c, uc, x_T)), non_blocking=True)
+
+        step_e2e_rgb()
+        ms_rgb = timed(step_e2e_rgb, args.steps) / args.steps
+        vae_info = {"decode_ms_per_8_images": ms_dec, "decode_tflops": b * VAE_GFLOP_PER_IMAGE / 1e3 / (ms_dec / 1e3),
+                    "e2e_rgb_images_per_sec": world * b / (ms_rgb / 1e3), "d2h_bytes_per_step": rgb_host.numel() * 4,
+                    "note": "sampling + decode_first_stage, host prompts/noise in, host 512x512 RGB out"}
+        del vae, lat
+        model.first_stage_model = None
+        torch.cuda.empty_cache()
+
     # ---- roofline of the dominant kernel: per-launch CUDA events over one eager UNet step --------------------
     peaks = measured_peaks()
     roofline, breakdown = None, None
@@ -321,6 +354,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
+            "vae_decode": vae_info,
             "clocks": clock_info,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

@@ -154,6 +154,14 @@ int af_linear_small(const float* x, const float* w, const float* bias, float* y,
                     int silu_out, af_stream_t stream);
 
 int af_cast_bf16(const float* x, void* y_bf16, long long n, af_stream_t stream);
+/* y[b,o,p] = bias[o] + sum_c w[o,c] * (in_scale * x[b,c,p]) over NCHW fp32 tensors with at most 4 channels: the VAE's
+ * post_quant_conv applied to z / scale_factor (ldm/models/autoencoder.py:331, ldm/models/diffusion/ddpm.py:1267). */
+int af_channel_mix4(const float* x_nchw, const float* w, const float* bias, float in_scale, int B, int Cin, int Cout,
+                    long long HW, float* y_nchw, af_stream_t stream);
+/* Row softmax of materialised scores for the VAE's single-head AttnBlock (ldm/modules/diffusionmodules/model.py:
+ * 188-193: softmax(q.k^T * c^-1/2, dim=2)): y[r][0..n) = softmax(scale * x[r][0..n)), fp32 in, bf16 out, n <= 16384. */
+int af_softmax_rows(const float* x, long long ldx, long long rows, int n, float scale, void* y_bf16, long long ldo,
+                    af_stream_t stream);
 /* F.interpolate(scale_factor=2, mode="nearest") (openaimodel.py:120) fused with the bf16 cast. */
 int af_upsample2x_cast(const float* x_nhwc, void* y_bf16, int B, int H, int W, int C, af_stream_t stream);
 
