@@ -300,8 +300,17 @@ def main():
         dom = max(tensor_names, key=lambda n: breakdown.get(n, {"ms": 0})["ms"])
         d = breakdown[dom]
         achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_unet_step_traffic.json")   # one ncu pass of the same UNet step
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath)).get(dom)
+            if tj and tj["launches"]:
+                traffic = tj["dram_bytes"] / tj["launches"]
+                traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu pass of scripts/unet_step.py "
+                               f"(profiles/r01_unet_step_traffic.json; algorithmic {tj['algorithmic_bytes'] / tj['launches']:.3e} B)")
         roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"],
-                    "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
+                    "traffic_source": traffic_src,
                     "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
                     "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
                     "share_of_unet_step": d["ms"] / step_ms,
