@@ -55,6 +55,7 @@ struct GemmParams {
   void* out;
   long long ldo;
   int out_bf16;
+  long long* trace;        // optional timeline of CTA 0: [3 actors][32 tiles][8 events] clock64 (af_gemm_set_trace)
   int geglu;               // tile cols [0,BN/2) = value, [BN/2,BN) = gate; writes BN/2 cols
   int act;                 // 0 none, 1 quick_gelu x*sigmoid(1.702x) on (acc + bias), before the residual add
   float* gn_stats;         // [slots_total][N][2] per-channel (sum, sumsq) over 32-row quarters of the output, or null
@@ -142,6 +143,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     m_tile = CTA2 ? 2 * pm + static_cast<int>(cta_rank) : pm;
   };
 
+  // timeline probe: actor 0 = TMA producer, 1 = MMA issuer, 2 = epilogue warp 0 (lane 0 each), CTA 0, first 32 tiles
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && lane == 0;
+  auto stamp = [&](int actor, int tile_no, int ev) {
+    if (tracing && tile_no < 32) p.trace[(actor * 32 + tile_no) * 8 + ev] = clock64();
+  };
+
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmA0);
     tma_prefetch_desc(&p.tmA1);
@@ -178,9 +185,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+      for (int tile = tile_first, tno = 0; tile < num_tiles; tile += tile_step, ++tno) {
         int n_tile, m_tile;
         tile_mn(tile, n_tile, m_tile);
+        stamp(0, tno, 0);
         const int n0 = n_tile * BN + (CTA2 ? static_cast<int>(cta_rank) * (BN / 2) : 0);
         int cw = 0, ch = 0, cn = 0;
         if (p.amode != 0) {
@@ -217,7 +225,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             stage = 0;
             phase ^= 1;
           }
+          if (kb == 0) stamp(0, tno, 1);
         }
+        stamp(0, tno, 2);
       }
     }
   } else if (warp == 1) {
@@ -228,13 +238,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+      for (int tile = tile_first, tno = 0; tile < num_tiles; tile += tile_step, ++tno) {
+        stamp(1, tno, 0);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
+        stamp(1, tno, 1);
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (kb == 0) stamp(1, tno, 2);
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t adesc = umma_desc_sw128(sa);
           const uint64_t bdesc = umma_desc_sw128(sa + Cfg::kABytes);
@@ -251,6 +264,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           }
         }
         if constexpr (CTA2) tc_commit2(&tfull_bar[acc]); else tc_commit(&tfull_bar[acc]);
+        stamp(1, tno, 3);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -268,13 +282,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     const int nch = (kOutCols - half * 32 + 63) / 64;                   // work items of this warp per tile
     const bool has_res = !GEGLU && p.residual != nullptr;
 
-    // (tile, chunk) of this warp's j-th work item -> TMA coordinates {col, c1, c2, c3} of its 32x32 box
-    auto item_coords = [&](int j, int& c0, int& c1, int& c2, int& c3) -> bool {
-      const int t = tile_first + (j / nch) * tile_step;
-      if (t >= num_tiles) return false;
-      int n_tile, m_tile;
+    // TMA row coordinates {c1, c2, c3} of this warp's 32-row box inside tile t (integer divisions by run-time values:
+    // done once per TILE, never per 32x32 work item - they used to cost ~1500 of the ~3000 cycles an item took,
+    // profiles/r01_gemm_epilogue_timeline.md)
+    auto tile_rows = [&](int t, int& n_tile, int& c1, int& c2, int& c3) {
+      int m_tile;
       tile_mn(t, n_tile, m_tile);
-      c0 = n_tile * kOutCols + half * 32 + 64 * (j % nch);
       if (p.amode == 0) {
         c1 = m_tile * 128 + q * 32; c2 = 0; c3 = 0;
       } else {
@@ -286,28 +299,42 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         c2 = th * p.bh + (r0 / p.bw) % p.bh;
         c3 = tn * p.nb + r0 / (p.bw * p.bh);
       }
-      return true;
     };
-    auto issue_res_load = [&](int j) {   // lane 0 only
-      int c0, c1, c2, c3;
-      if (!item_coords(j, c0, c1, c2, c3)) return;
-      const int sl = j % SLOTS;
+    // residual prefetch cursor: walks this warp's work items (tile, chunk) in order, kAhead items in front
+    int pf_tile = tile_first, pf_i = 0, pf_n = 0, pf_c1 = 0, pf_c2 = 0, pf_c3 = 0, pf_item = 0;
+    if (pf_tile < num_tiles) tile_rows(pf_tile, pf_n, pf_c1, pf_c2, pf_c3);
+    auto issue_res_load = [&]() {   // lane 0 only
+      if (pf_tile >= num_tiles) return;
+      const int sl = pf_item % SLOTS;
       mbar_arrive_expect_tx(&my_res_bar[sl], 4096);
-      tma_load_4d(my_slots + sl * Cfg::kSlotBytes, &p.tmRes, &my_res_bar[sl], c0, c1, c2, c3);
+      tma_load_4d(my_slots + sl * Cfg::kSlotBytes, &p.tmRes, &my_res_bar[sl], pf_n * kOutCols + half * 32 + 64 * pf_i,
+                  pf_c1, pf_c2, pf_c3);
+      ++pf_item;
+      if (++pf_i == nch) {
+        pf_i = 0;
+        pf_tile += tile_step;
+        if (pf_tile < num_tiles) tile_rows(pf_tile, pf_n, pf_c1, pf_c2, pf_c3);
+      }
     };
     // residual prefetch distance: SLOTS - 1 items (SLOTS == 1: the next load waits for this item's store to drain)
     constexpr int kAhead = SLOTS > 1 ? SLOTS - 1 : 1;
     if (has_res && lane == 0) {
 #pragma unroll
-      for (int j = 0; j < kAhead; ++j) issue_res_load(j);
+      for (int j = 0; j < kAhead; ++j) issue_res_load();
     }
 
     int item = 0;                      // running work-item index of this warp (slot = item % SLOTS)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+    for (int tile = tile_first, tno = 0; tile < num_tiles; tile += tile_step, ++tno) {
       int n_tile, m_tile;
       tile_mn(tile, n_tile, m_tile);
+      if (ew == 0) stamp(2, tno, 0);
+      int c1, c2, c3;
+      {
+        int nt;
+        tile_rows(tile, nt, c1, c2, c3);
+      }
       // this lane's output row (for the per-sample rowbias and the statistics mask)
       bool row_ok;
       uint32_t grow;
@@ -335,15 +362,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (ew == 0) stamp(2, tno, 1);
       const uint32_t t_acc = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
 
-      for (int i = 0; i < nch; ++i, ++item) {
+      // (Fetching chunk i+1 from TMEM into a second register set while chunk i is staged was measured SLOWER: 48.7 ->
+      // 59.4 us on M65536 N320 K320 +res, the conversion phase doubles - profiles/r01_gemm_epilogue_timeline.md.)
+      for (int i = 0; i < nch; ++i) {
         const int c = half * 32 + 64 * i;                    // first accumulator column of the chunk
         const int col0 = n_tile * kOutCols + c;              // first output column
         const int sl = item % SLOTS;
         uint8_t* slot = my_slots + sl * Cfg::kSlotBytes;
-        int c0, c1, c2, c3;
-        item_coords(item, c0, c1, c2, c3);
+        const int c0 = col0;
 
         if constexpr (GEGLU) {
           // out[:, j] = (acc[:, j] + bv[j]) * gelu(acc[:, BN/2 + j] + bg[j]) -> bf16, 64-byte rows, SWIZZLE_64B
@@ -401,6 +430,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             __syncwarp();
           }
           tmem_ld_wait();
+          if (ew == 0 && i == 0) stamp(2, tno, 2);
           float4 o[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -443,16 +473,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             if (stat_slot >= 0 && col0 + lane < p.N)
               *reinterpret_cast<float2*>(p.gn_stats + (stat_slot * p.N + col0 + lane) * 2) = make_float2(s, ss);
           }
+          if (ew == 0 && i == 0) stamp(2, tno, 3);
           if (lane == 0) {
             if (col_ok) tma_store_4d(&p.tmOut, slot, c0, c1, c2, c3);
             bulk_commit();
             if (has_res) {
               bulk_wait_read<(SLOTS > 1 ? 1 : 0)>();         // the previous item's store has drained its slot ...
-              issue_res_load(item + kAhead);                 // ... which is the slot of item + kAhead
+              issue_res_load();                              // ... which is the slot of item + kAhead
             }
           }
+          if (ew == 0 && i == 0) stamp(2, tno, 4);
         }
+        ++item;
       }
+      if (ew == 0) stamp(2, tno, 5);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -478,6 +512,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+static long long* g_gemm_trace = nullptr;
 static int g_pair_mode = 1;   // 1: CTA pairs (cta_group::2) whenever a GEMM has at least two 128-row tiles; 0: never
 
 template <int BN, bool GEGLU, int SLOTS, bool CTA2>
@@ -622,6 +657,11 @@ static int fill_epilogue(GemmParams& p, const af_epilogue* ep, long long default
 
 using namespace af;
 
+extern "C" int af_gemm_set_trace(long long* device_buffer) {
+  af::g_gemm_trace = device_buffer;
+  return 0;
+}
+
 extern "C" int af_gemm_set_pair_mode(int mode) {
   const int old = g_pair_mode;
   g_pair_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
@@ -638,6 +678,7 @@ extern "C" int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* 
                "af_gemm_bf16: K / lda must be multiples of 8 (16-byte TMA strides)");
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  p.trace = g_gemm_trace;
   const int K = K0 + K1;
   const int bn = pick_bn(N, ep->geglu, bn_hint);
   const bool pair = want_pair((M + 127) / 128, (N + bn - 1) / bn, bn, 0);
@@ -708,6 +749,7 @@ extern "C" int af_conv3x3_bf16(const void* X0, int C0, const void* X1, int C1, c
   AF_CHECK_ARG(!ep->geglu, "af_conv3x3_bf16: geglu epilogue unsupported");
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  p.trace = g_gemm_trace;
   const int Cin = C0 + C1;
   const int Ho = stride == 1 ? H : H / 2, Wo = stride == 1 ? W : W / 2;
   const int bn = pick_bn(Cout, 0, bn_hint);

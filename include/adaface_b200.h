@@ -72,6 +72,13 @@ int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* A1, long lo
  * measured to win (linear GEMMs, N tile >= 160, >= 2 waves), 2 = pair wherever legal.  Returns the previous mode.
  * Results are bit-identical between the modes (same accumulation order). */
 int af_gemm_set_pair_mode(int mode);
+/* Timeline probe of af_gemm_bf16 / af_conv3x3_bf16 (measurement aid, results unaffected): with a non-null
+ * device_buffer (>= 3*32*8 int64, caller-owned) CTA 0 of every following launch records clock64 stamps
+ * [actor: TMA producer, MMA issuer, epilogue warp 0][its first 32 tiles][8 events]
+ * (producer: tile begin, first stage issued, last stage issued; MMA: begin, accumulator free, first stage landed, tile
+ * committed; epilogue: tile begin, accumulator full, first chunk in registers, first chunk in smem, first store issued,
+ * tile done).  Null switches it off. */
+int af_gemm_set_trace(long long* device_buffer);
 
 /* Schedule of the two-query-tile self-attention kernel (head dims 40 / 80, Nq >= 256), for A/B measurements:
  * bit 0 = hand P to the PV MMA per 64-key piece instead of per key block, bit 1 = pass P through tensor memory
