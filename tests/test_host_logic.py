@@ -113,3 +113,30 @@ def test_packing_layouts():
     pq = pack_qk(wq, wq, 8)
     assert pq.shape == (2 * 8 * 48, 320)
     assert float(pq.view(2, 8, 48, 320)[:, :, 40:].abs().max()) == 0.0   # zero pad rows -> zero pad columns
+
+
+# ------------------------------------------------------------------------------------------------ txt2img CLI (row N3)
+def test_txt2img_cli_host_logic(tmp_path):
+    from adaprompt_b200 import txt2img as t2i
+    a = t2i.parse_args(["--synthetic", "--scale", "4", "1", "--n_samples", "3"])
+    assert a.scale == [4.0, 1.0] and a.ddim_steps == 50 and a.subject_string == "z"
+    assert t2i.parse_args(["--synthetic", "--scale", "5"]).scale == [5.0, 5.0]
+    with pytest.raises(SystemExit):
+        t2i.parse_args(["--prompt", "x"])                      # neither --ckpt nor --synthetic
+    assert t2i.expand_prompt("a photo of a z in a park", "z", 4) == "a photo of a z , , ,  in a park".replace("  ", " ") \
+        or t2i.expand_prompt("a photo of a z in a park", "z", 4).split() == "a photo of a z , , , in a park".split()
+    tok = t2i.HashTokenizer()
+    ids = tok(["a photo of a z, , ,", "hello world"]).input_ids
+    assert ids.shape == (2, 77) and ids[0, 0] == t2i.BOS and ids[0, 5] == t2i.TOK_Z and ids[0, 6] == t2i.TOK_COMMA
+    assert (ids[1, 3:] == t2i.EOS).all() and tok.encode("z")[0] == t2i.TOK_Z
+    sd = {"state_dict": {"model.diffusion_model.out.2.bias": torch.zeros(4), "first_stage_model.decoder.conv_in.bias": torch.zeros(512),
+                         "cond_stage_model.transformer.text_model.final_layer_norm.bias": torch.zeros(768), "model_ema.decay": torch.zeros(())}}
+    parts = t2i.split_sd15_checkpoint(sd)
+    assert list(parts["unet"]) == ["out.2.bias"] and list(parts["vae"]) == ["decoder.conv_in.bias"]
+    assert list(parts["clip"]) == ["text_model.final_layer_norm.bias"]
+    imgs = torch.rand(3, 3, 16, 16)
+    paths = t2i.save_images(imgs, str(tmp_path / "s"), 7, "r0")
+    t2i.save_grid(imgs, str(tmp_path / "g.png"), 2)
+    from PIL import Image
+    assert [p.split("-")[-1] for p in paths] == ["00007.png", "00008.png", "00009.png"]
+    assert Image.open(str(tmp_path / "g.png")).size == (32, 32)

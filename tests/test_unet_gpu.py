@@ -75,6 +75,26 @@ def test_unet_eps_vs_oracle_fresh_inputs(unet, state_dict):
     assert _rel(eps, ref) < EPS_TOL
 
 
+@pytest.mark.parametrize("hw", [(96, 96), (40, 24)])
+def test_unet_eps_vs_oracle_other_resolutions(unet, state_dict, hw):
+    """BASELINE.json config #5 geometry: 768^2 images = 96x96 latents (9216 / 2304 / 576 / 144 self-attention tokens -
+    the 144-token level is not a multiple of the 128-row query tile), plus a non-square latent with ragged conv tiles."""
+    from oracle.golden_inputs import EXTRA_INFO
+    from oracle.unet_oracle import UNetSpec, unet_forward
+    g = torch.Generator().manual_seed(7 + hw[0])
+    x = torch.randn(1, 4, hw[0], hw[1], generator=g)
+    t = torch.tensor([401])
+    ctx = torch.randn(16, 77, 768, generator=g)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    with torch.no_grad():
+        ref = unet_forward(state_dict, UNetSpec(), x, t, ctx, dict(EXTRA_INFO))
+        eps = unet(x.cuda(), t.cuda(), context=ctx.cuda(), extra_info=dict(EXTRA_INFO))
+    err = _rel(eps, ref)
+    print(f"unet eps {hw[0]}x{hw[1]}: rel-L2 {err:.3e}")
+    assert eps.shape == ref.shape
+    assert err < EPS_TOL
+
+
 def test_modules_vs_reference_golden(unet):
     from oracle.golden_inputs import module_inputs
     gold = torch.load(os.path.join(GOLD, "modules.pt"))

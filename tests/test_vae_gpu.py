@@ -99,3 +99,21 @@ def test_vae_decode_512px_properties(vae_and_sd):
     torch.cuda.synchronize()
     assert a.shape == (1, 3, 512, 512) and torch.isfinite(a).all()
     assert torch.equal(a, b)
+
+
+def test_txt2img_cli_end_to_end_synthetic(tmp_path):
+    """Row N3: prompts -> conditioning (ID tokens spliced) -> DDIM with annealed CFG -> decode_first_stage -> PNGs,
+    through the command-line entry point on random-init weights of the real architecture."""
+    from PIL import Image
+    from adaprompt_b200 import _lib, txt2img
+    n0 = _lib.TRACE.count
+    txt2img.main(["--synthetic", "--synthetic_clip_layers", "2", "--prompt", "a photo of a z in a park", "--ddim_steps", "3",
+                  "--n_samples", "2", "--H", "256", "--W", "256", "--scale", "4", "1", "--outdir", str(tmp_path),
+                  "--no_cuda_graph", "--save_latents"])
+    assert _lib.TRACE.count - n0 > 1000
+    files = sorted(os.listdir(tmp_path / "samples"))
+    assert [f for f in files if f.endswith(".png")] == ["r0-00000.png", "r0-00001.png"]
+    assert Image.open(str(tmp_path / "samples" / "r0-00000.png")).size == (256, 256)
+    assert Image.open(str(tmp_path / "grid-r0.png")).size == (512, 256)
+    lat = torch.load(str(tmp_path / "samples" / "r0-00000-latents.pt"))
+    assert lat.shape == (2, 4, 32, 32) and torch.isfinite(lat).all()
