@@ -299,14 +299,27 @@ def clip_grad_norm(params: Sequence[torch.nn.Parameter], max_norm: float = 0.5) 
     return total
 
 
+class _QSampleOnly:
+    """The two things Arc2FaceTeacher.forward reads from the LatentDiffusion object (ddpm.py:5448,5456)."""
+
+    def __init__(self, alphas_cumprod: torch.Tensor):
+        self.alphas_cumprod = alphas_cumprod
+
+    def q_sample(self, x0, t, noise):
+        a = self.alphas_cumprod[t].view(-1, 1, 1, 1)
+        return a.sqrt() * x0 + (1 - a).sqrt() * noise
+
+
 class DistillStep:
     """One Stage-1 zero-shot distillation micro-step (ddpm.py:2953-3039 with num_denoising_steps = 1):
     x_noisy = sqrt(a_t) x0 + sqrt(1 - a_t) noise (:416-419) -> student UNet with the AdaFace prompt ->
-    MSE against the teacher's noise prediction.  The teacher (Arc2Face UNet, ddpm.py:5402-5478) is SURVEY.md
-    section 8(f) N4; its eps is an input here."""
+    MSE against the teacher's noise prediction.  The teacher's eps is either an input (`teacher_eps` in the batch) or
+    computed by `teacher` = arc2face_teacher.Arc2FaceTeacher (ddpm.py:5402-5478) on the
+    21-token Arc2Face ID prompt (ddpm.py:5427) when the batch carries none."""
 
     def __init__(self, unet, frozen_tm: CLIPTextTransformer, sbg, arc2face_text_encoder, tokenizer, alphas_cumprod,
-                 placeholder_token: int, extra_info: Optional[dict] = None):
+                 placeholder_token: int, extra_info: Optional[dict] = None, teacher=None):
+        self.teacher = teacher
         self.unet, self.frozen_tm, self.sbg = unet, frozen_tm, sbg
         self.arc2face, self.tokenizer = arc2face_text_encoder, tokenizer
         self.acp = torch.as_tensor(alphas_cumprod, dtype=torch.float32)
@@ -324,12 +337,26 @@ class DistillStep:
         subj, _ = sbg_forward_train(self.sbg, id_embs)
         return conditioning_train(self.frozen_tm, tokens, subj, self.placeholder_token)
 
+    @torch.no_grad()
+    def teacher_eps(self, x0, t, noise, face_embs) -> torch.Tensor:
+        """ddpm.py:2953-3002 with num_denoising_steps = 1: the teacher denoises the same x_noisy, conditioned on the
+        Arc2Face ID prompt embeddings with all padding removed (input_max_length = 21)."""
+        if self.teacher is None:
+            raise RuntimeError("DistillStep: the batch has no teacher_eps and no teacher model was given")
+        prompt_embs, _ = arc2face_forward_face_embs(self.tokenizer, self.arc2face, face_embs, input_max_length=21,
+                                                    return_full_and_core_embs=True)
+        ddpm = _QSampleOnly(self.acp.to(x0.device))
+        preds, _, _, _ = self.teacher(ddpm, x0, noise, t, prompt_embs, num_denoising_steps=1)
+        return preds[0]
+
     def loss(self, x0, t, noise, teacher_eps, face_embs, tokens) -> torch.Tensor:
+        if teacher_eps is None:
+            teacher_eps = self.teacher_eps(x0, t, noise, face_embs)
         c = self.context(face_embs, tokens)
         eps = unet_forward_train(self.unet, self.q_sample(x0, t, noise), t, c, dict(self.extra_info))
         return distill_loss(eps, teacher_eps)
 
     def micro_step(self, batch: Dict[str, torch.Tensor], accum: int = 1) -> float:
-        loss = self.loss(batch["x0"], batch["t"], batch["noise"], batch["teacher_eps"], batch["face_embs"], batch["tokens"])
+        loss = self.loss(batch["x0"], batch["t"], batch["noise"], batch.get("teacher_eps"), batch["face_embs"], batch["tokens"])
         (loss / accum).backward()
         return float(loss.detach())

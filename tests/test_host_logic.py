@@ -140,3 +140,76 @@ def test_txt2img_cli_host_logic(tmp_path):
     from PIL import Image
     assert [p.split("-")[-1] for p in paths] == ["00007.png", "00008.png", "00009.png"]
     assert Image.open(str(tmp_path / "g.png")).size == (32, 32)
+
+
+# ------------------------------------------------------------------------------------------------ Arc2Face teacher (row N4)
+def test_diffusers_unet_key_map_is_a_bijection_onto_the_unet():
+    from adaprompt_b200.arc2face_teacher import (convert_diffusers_unet_state_dict,
+                                                 convert_ldm_unet_state_dict_to_diffusers)
+    from adaprompt_b200.ldm_lite import SD15_UNET_CONFIG
+    from adaprompt_b200.unet import UNetModel
+    with torch.device("meta"):
+        unet = UNetModel(**SD15_UNET_CONFIG)
+    sd = unet.state_dict()
+    hf = convert_ldm_unet_state_dict_to_diffusers(sd)
+    assert len(hf) == len(sd) == len(set(hf))
+    for k in ("conv_in.weight", "time_embedding.linear_2.bias", "down_blocks.0.resnets.1.time_emb_proj.weight",
+              "down_blocks.2.downsamplers.0.conv.weight", "down_blocks.3.resnets.0.norm1.weight",
+              "mid_block.attentions.0.transformer_blocks.0.attn2.to_k.weight", "mid_block.resnets.1.conv2.bias",
+              "up_blocks.0.upsamplers.0.conv.weight", "up_blocks.1.resnets.0.conv_shortcut.weight",
+              "up_blocks.3.attentions.2.proj_out.weight", "conv_norm_out.weight", "conv_out.bias"):
+        assert k in hf, k
+    assert not any(k.startswith(("input_blocks", "output_blocks", "middle_block", "out.", "time_embed.")) for k in hf)
+    back = convert_diffusers_unet_state_dict(hf)
+    assert list(back) == list(sd) and all(back[k].shape == sd[k].shape for k in sd)
+    # Linear-style 1x1 projections of newer diffusers checkpoints are reshaped to the reference's Conv2d layout
+    k = "mid_block.attentions.0.proj_in.weight"
+    hf2 = dict(hf); hf2[k] = torch.empty(1280, 1280, device="meta")
+    assert convert_diffusers_unet_state_dict(hf2)["middle_block.1.proj_in.weight"].shape == (1280, 1280, 1, 1)
+    with pytest.raises(KeyError):
+        convert_diffusers_unet_state_dict({"class_embedding.weight": torch.empty(1)})
+
+
+def test_arc2face_teacher_multi_step_logic():
+    """ddpm.py:5434-5480 restated by hand for 3 denoising steps with a stand-in UNet (same RNG call order)."""
+    from adaprompt_b200.arc2face_teacher import Arc2FaceTeacher
+    from adaprompt_b200.ldm_lite import LatentDiffusionLite
+
+    class FakeUNet(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.tensor(0.3))
+            self.calls = []
+
+        def forward(self, x, t, context=None, extra_info=None):
+            self.calls.append((tuple(context.shape), t.clone()))
+            return self.w * x + 0.01 * t.view(-1, 1, 1, 1).float() / 1000 + context.mean()
+
+    ldm = LatentDiffusionLite(unet=torch.nn.Identity())
+    fake = FakeUNet()
+    teacher = Arc2FaceTeacher(fake)
+    g = torch.Generator().manual_seed(5)
+    x0, noise = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g)
+    t, ctx = torch.tensor([800, 500]), torch.randn(2, 21, 768, generator=g)
+    torch.manual_seed(11)
+    preds, x0s, noises, ts = teacher(ldm, x0, noise, t, ctx, num_denoising_steps=3)
+    assert len(preds) == 3 and len(x0s) == 3 and len(noises) == 3 and len(ts) == 3
+    assert fake.calls[0][0] == (32, 21, 768)                      # one copy of the context per cross-attention layer
+    assert all((ts[i + 1] < ts[i]).all() for i in range(2))
+    # hand restatement
+    torch.manual_seed(11)
+    acp = ldm.alphas_cumprod
+    xs, ns, tt = [x0], [noise], [t]
+    for i in range(3):
+        a = acp[tt[i]].view(-1, 1, 1, 1)
+        xn = a.sqrt() * xs[i] + (1 - a).sqrt() * ns[i]
+        pr = 0.3 * xn + 0.01 * tt[i].view(-1, 1, 1, 1).float() / 1000 + ctx.repeat_interleave(16, 0).mean()
+        assert torch.allclose(pr, preds[i], atol=1e-6)
+        xs.append(torch.sqrt(1.0 / a) * xn - torch.sqrt(1.0 / a - 1) * pr)
+        assert torch.allclose(xs[-1], x0s[i], atol=1e-5)
+        if i < 2:
+            r = torch.rand_like(tt[i].float())
+            lb, ub = tt[i] * np.power(0.5, np.power(2, -0.3)), tt[i] * np.power(0.7, np.power(2, -0.3))
+            tt.append(((ub - lb) * r + lb).long())
+            assert torch.equal(tt[-1], ts[i + 1])
+            ns.append(torch.randn_like(xs[-1]))

@@ -447,3 +447,43 @@ def test_prodigy_matches_reference_golden(case):
         assert abs(opt.param_groups[0]["d"] - g["d"][step]) <= 2e-4 * abs(g["d"][step]), (step, opt.param_groups[0]["d"], g["d"][step])
     for p, ref in zip(params, g["final"]):
         assert _rel(p, ref) < 1e-4
+
+
+def test_distill_step_computes_teacher_eps_when_the_batch_has_none():
+    """Row N4 wired into T1: without `teacher_eps` in the batch, DistillStep asks the Arc2Face teacher (a second UNet
+    conditioned on the 21-token Arc2Face ID prompt, ddpm.py:5427,5451) for the target; the loss equals the one computed
+    from the fp32 oracle's teacher prediction."""
+    from adaprompt_b200.arc2face_teacher import Arc2FaceTeacher
+    from adaprompt_b200.train_cond import DistillStep
+    from oracle import text_oracle as to
+    from oracle.golden_inputs import EXTRA_INFO
+    from oracle.unet_oracle import UNetSpec, make_alphas_cumprod, unet_forward
+    from test_text_gpu import StubTokenizer
+    unet, sd_unet = _unet()
+    sbg, sd_sbg = _sbg_small(31, 2)
+    frozen, sd_frozen = _clip_small(32, 2)
+    arc2face, sd_arc = _clip_small(33, 2)
+    frozen.text_model.last_layers_skip_weights = [0.5, 0.5]
+    acp = torch.tensor(make_alphas_cumprod(), dtype=torch.float32)
+    step = DistillStep(unet, frozen.text_model, sbg, arc2face.eval(), StubTokenizer(), acp, to.TOK_Z,
+                       teacher=Arc2FaceTeacher(unet))
+    g = torch.Generator().manual_seed(19)
+    B = 2
+    batch = {"x0": torch.randn(B, 4, 32, 32, generator=g), "noise": torch.randn(B, 4, 32, 32, generator=g),
+             "t": torch.tensor([451, 77]), "face_embs": F.normalize(torch.randn(B, 512, generator=g), dim=-1),
+             "tokens": torch.tensor([to.subject_prompt_ids(77)] * B)}
+    cuda = {k: v.cuda() for k, v in batch.items()}
+    t_eps = step.teacher_eps(cuda["x0"], cuda["t"], cuda["noise"], cuda["face_embs"])
+    with torch.no_grad():
+        ctx21, _ = to.arc2face_forward_face_embs(sd_arc, batch["face_embs"], input_max_length=21)
+        a = acp[batch["t"]].view(-1, 1, 1, 1)
+        x_noisy = a.sqrt() * batch["x0"] + (1 - a).sqrt() * batch["noise"]
+        t_ref = unet_forward(sd_unet, UNetSpec(), x_noisy, batch["t"], ctx21.repeat_interleave(16, 0), dict(EXTRA_INFO))
+    assert tuple(ctx21.shape) == (B, 21, 768)
+    e = _rel(t_eps, t_ref)
+    print(f"teacher eps rel-L2 {e:.3e}")
+    assert e < 1e-2
+    for p in unet.parameters():                      # Arc2FaceTeacher froze the shared UNet: the student path needs no weight grads either
+        assert not p.requires_grad
+    loss = step.micro_step(cuda)
+    assert loss > 0 and all(torch.isfinite(p.grad).all() for p in sbg.prompt2token_proj.parameters() if p.grad is not None)

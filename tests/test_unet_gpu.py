@@ -213,3 +213,35 @@ def test_adaface_wrapper_forward_samples_latents(unet):
     assert lat.shape == (2, 4, 32, 32) and torch.isfinite(lat).all()
     lat1 = w(noise, "a photo of z in a park", guidance_scale=1.0, out_image_count=2)   # g == 1: uncond branch skipped
     assert torch.isfinite(lat1).all() and not torch.equal(lat, lat1)
+
+
+def test_arc2face_teacher_on_the_cuda_unet(unet, state_dict):
+    """Row N4: the distillation teacher = this UNet with weights delivered in the diffusers key layout and ONE plain
+    21-token context (ddpm.py:5427,5451) instead of the layerwise 77-token one; its noise prediction equals the fp32
+    oracle fed the same context once per layer."""
+    from adaprompt_b200.arc2face_teacher import (Arc2FaceTeacher, convert_diffusers_unet_state_dict,
+                                                 convert_ldm_unet_state_dict_to_diffusers)
+    from adaprompt_b200.ldm_lite import SD15_UNET_CONFIG, LatentDiffusionLite
+    from adaprompt_b200.unet import UNetModel
+    from oracle.golden_inputs import EXTRA_INFO
+    from oracle.unet_oracle import UNetSpec, unet_forward
+    with torch.device("meta"):
+        t_unet = UNetModel(**SD15_UNET_CONFIG)
+    t_unet = t_unet.to_empty(device="cuda")
+    hf = convert_ldm_unet_state_dict_to_diffusers(unet.state_dict())          # what a diffusers checkpoint looks like
+    t_unet.load_state_dict(convert_diffusers_unet_state_dict(hf))
+    t_unet.eval()
+    teacher = Arc2FaceTeacher(t_unet)
+    ldm = LatentDiffusionLite(unet=torch.nn.Identity()).cuda()
+    g = torch.Generator().manual_seed(21)
+    x0, noise = torch.randn(2, 4, 32, 32, generator=g), torch.randn(2, 4, 32, 32, generator=g)
+    t, ctx = torch.tensor([700, 300]), torch.randn(2, 21, 768, generator=g)
+    preds, x0s, _, ts = teacher(ldm, x0.cuda(), noise.cuda(), t.cuda(), ctx.cuda(), num_denoising_steps=2)
+    assert len(preds) == 2 and (ts[1] < ts[0]).all() and all(torch.isfinite(p).all() for p in preds + x0s)
+    a = ldm.alphas_cumprod.cpu()[t].view(-1, 1, 1, 1)
+    x_noisy = a.sqrt() * x0 + (1 - a).sqrt() * noise
+    with torch.no_grad():
+        ref = unet_forward(state_dict, UNetSpec(), x_noisy, t, ctx.repeat_interleave(16, 0), dict(EXTRA_INFO))
+    err = _rel(preds[0], ref)
+    print(f"teacher eps (21-token context): rel-L2 {err:.3e}")
+    assert err < EPS_TOL
