@@ -187,15 +187,23 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   const uint32_t end = min(total, begin + per_block);
   const float* xb0 = x0 + static_cast<size_t>(b) * HW * C0;
   const float* xb1 = C1 ? x1 + static_cast<size_t>(b) * HW * C1 : nullptr;
-  auto src_of = [&](uint32_t i, int& c) -> const float* {
-    if (C1 == 0) {  // single source: the input is as dense as the output
-      c = static_cast<int>(i % static_cast<uint32_t>(cq)) * 4;
-      return xb0 + static_cast<size_t>(i) * 4;
-    }
-    const uint32_t p = i / static_cast<uint32_t>(cq);
-    c = static_cast<int>(i - p * cq) * 4;
+  // channel quad / pixel of a flat quad index are tracked incrementally (the thread advances by 256 quads per step):
+  // no integer division by the run-time channel count in the loop
+  const uint32_t ucq = static_cast<uint32_t>(cq);
+  const uint32_t step_q = 256u % ucq, step_p = 256u / ucq;
+  auto src_at = [&](uint32_t i, uint32_t p, uint32_t q) -> const float* {   // q = i % cq, p = i / cq
+    const int c = static_cast<int>(q) * 4;
+    if (C1 == 0) return xb0 + static_cast<size_t>(i) * 4;            // single source: as dense as the output
     if (c < C0) return xb0 + static_cast<size_t>(p) * C0 + c;
     return xb1 + static_cast<size_t>(p) * C1 + (c - C0);
+  };
+  auto advance = [&](uint32_t& p, uint32_t& q) {
+    q += step_q;
+    p += step_p;
+    if (q >= ucq) {
+      q -= ucq;
+      ++p;
+    }
   };
   auto emit = [&](uint32_t i, int c, const float4& v) {
     const float4 a = *reinterpret_cast<const float4*>(s_ab + c);
@@ -220,18 +228,30 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
     }
   };
   uint32_t i = begin + threadIdx.x;
+  uint32_t p0 = i / ucq, q0 = i - p0 * ucq;
   for (; i + 768 < end; i += 1024) {  // four independent 16-byte loads in flight per thread
-    int c0, c1, c2, c3;
-    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src_of(i, c0)));
-    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src_of(i + 256, c1)));
-    const float4 v2 = __ldg(reinterpret_cast<const float4*>(src_of(i + 512, c2)));
-    const float4 v3 = __ldg(reinterpret_cast<const float4*>(src_of(i + 768, c3)));
-    emit(i, c0, v0); emit(i + 256, c1, v1); emit(i + 512, c2, v2); emit(i + 768, c3, v3);
+    uint32_t p1 = p0, q1 = q0;
+    advance(p1, q1);
+    uint32_t p2 = p1, q2 = q1;
+    advance(p2, q2);
+    uint32_t p3 = p2, q3 = q2;
+    advance(p3, q3);
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src_at(i, p0, q0)));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src_at(i + 256, p1, q1)));
+    const float4 v2 = __ldg(reinterpret_cast<const float4*>(src_at(i + 512, p2, q2)));
+    const float4 v3 = __ldg(reinterpret_cast<const float4*>(src_at(i + 768, p3, q3)));
+    emit(i, static_cast<int>(q0) * 4, v0);
+    emit(i + 256, static_cast<int>(q1) * 4, v1);
+    emit(i + 512, static_cast<int>(q2) * 4, v2);
+    emit(i + 768, static_cast<int>(q3) * 4, v3);
+    p0 = p3;
+    q0 = q3;
+    advance(p0, q0);
   }
   for (; i < end; i += 256) {
-    int c;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(src_of(i, c)));
-    emit(i, c, v);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src_at(i, p0, q0)));
+    emit(i, static_cast<int>(q0) * 4, v);
+    advance(p0, q0);
   }
 }
 

@@ -107,7 +107,7 @@ def test_txt2img_cli_end_to_end_synthetic(tmp_path):
     from PIL import Image
     from adaprompt_b200 import _lib, txt2img
     n0 = _lib.TRACE.count
-    txt2img.main(["--synthetic", "--synthetic_clip_layers", "2", "--prompt", "a photo of a z in a park", "--ddim_steps", "3",
+    txt2img.main(["--synthetic", "--synthetic_clip_layers", "2", "--prompt", "a photo of a z in a park", "--ddim_steps", "4",
                   "--n_samples", "2", "--H", "256", "--W", "256", "--scale", "4", "1", "--outdir", str(tmp_path),
                   "--no_cuda_graph", "--save_latents"])
     assert _lib.TRACE.count - n0 > 1000
