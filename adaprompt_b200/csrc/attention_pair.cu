@@ -749,15 +749,17 @@ __global__ void __launch_bounds__(640, 1) attention_rowsplit_kernel(const __grid
         }
         tmem_st16q(pt_addr + c / 2, pk);
       }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t * 2 + half]);
+      // the turn is handed over as soon as the last ex2 has been issued: the TMEM-store drain, fences and the
+      // mbarrier arrive below run under the other tile's ex2 phase
       if (pingpong) {
         if (t == 0) asm volatile("bar.arrive 10, 512;" ::: "memory");
         else if (j != n_blocks - 1) asm volatile("bar.arrive 9, 512;" ::: "memory");
       }
       if (tr_warp) stamp(t, j, 6);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t * 2 + half]);
       l_run = l_run * alpha + ((l4[0] + l4[1]) + (l4[2] + l4[3]));
     }
     // epilogue: l = l(half 0) + l(half 1); O / l -> bf16, 16-column chunks alternate between the two threads of the row

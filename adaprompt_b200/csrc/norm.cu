@@ -172,13 +172,15 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   const int cpg = C / kGroups;
   const int b = blockIdx.y;
   const float2* mr = reinterpret_cast<const float2*>(mean_rstd) + static_cast<size_t>(b) * kGroups;
-  for (int c = threadIdx.x; c < C; c += 256) {
-    const float2 m = __ldg(mr + c / cpg);
-    const float a = m.y * gamma[c];
-    s_ab[c] = a;
-    s_ab[C + c] = beta[c] - m.x * a;
-  }
-  __syncthreads();
+  auto prologue = [&]() {   // per-channel scale / shift of this sample; runs UNDER the first streaming loads
+    for (int c = threadIdx.x; c < C; c += 256) {
+      const float2 m = __ldg(mr + c / cpg);
+      const float a = m.y * gamma[c];
+      s_ab[c] = a;
+      s_ab[C + c] = beta[c] - m.x * a;
+    }
+    __syncthreads();
+  };
 
   const int cq = C >> 2;
   const uint32_t total = static_cast<uint32_t>(HW) * cq;   // quads per sample (< 2^31: 32-bit index math)
@@ -229,28 +231,42 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   };
   uint32_t i = begin + threadIdx.x;
   uint32_t p0 = i / ucq, q0 = i - p0 * ucq;
-  for (; i + 768 < end; i += 1024) {  // four independent 16-byte loads in flight per thread
-    uint32_t p1 = p0, q1 = q0;
-    advance(p1, q1);
-    uint32_t p2 = p1, q2 = q1;
-    advance(p2, q2);
-    uint32_t p3 = p2, q3 = q2;
-    advance(p3, q3);
-    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src_at(i, p0, q0)));
-    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src_at(i + 256, p1, q1)));
-    const float4 v2 = __ldg(reinterpret_cast<const float4*>(src_at(i + 512, p2, q2)));
-    const float4 v3 = __ldg(reinterpret_cast<const float4*>(src_at(i + 768, p3, q3)));
-    emit(i, static_cast<int>(q0) * 4, v0);
-    emit(i + 256, static_cast<int>(q1) * 4, v1);
-    emit(i + 512, static_cast<int>(q2) * 4, v2);
-    emit(i + 768, static_cast<int>(q3) * 4, v3);
-    p0 = p3;
-    q0 = q3;
-    advance(p0, q0);
+  // Double-buffered stream: the four 16-byte loads of step k+1 are issued before step k is normalised and stored
+  // (8 loads in flight per thread), and the very first group is in flight while the block computes its scale / shift.
+  float4 v[4];
+  uint32_t qv[4];
+  auto load4 = [&](uint32_t at, float4 (&vv)[4], uint32_t (&qq)[4]) {   // consumes and advances (p0, q0)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      qq[u] = q0;
+      vv[u] = __ldg(reinterpret_cast<const float4*>(src_at(at + 256u * u, p0, q0)));
+      advance(p0, q0);
+    }
+  };
+  bool have = i + 768 < end;
+  if (have) load4(i, v, qv);
+  prologue();
+  while (have) {
+    const uint32_t ni = i + 1024;
+    const bool have_next = ni + 768 < end;
+    float4 vn[4];
+    uint32_t qn[4];
+    if (have_next) load4(ni, vn, qn);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(i + 256u * u, static_cast<int>(qv[u]) * 4, v[u]);
+    if (have_next) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u] = vn[u];
+        qv[u] = qn[u];
+      }
+    }
+    i = ni;
+    have = have_next;
   }
   for (; i < end; i += 256) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(src_at(i, p0, q0)));
-    emit(i, static_cast<int>(q0) * 4, v);
+    const float4 t = __ldg(reinterpret_cast<const float4*>(src_at(i, p0, q0)));
+    emit(i, static_cast<int>(q0) * 4, t);
     advance(p0, q0);
   }
 }
@@ -365,7 +381,7 @@ extern "C" int af_groupnorm_apply(const float* x0, int C0, const float* x1, int 
   AF_CHECK_ARG(C <= 5120, "af_groupnorm_apply: C=%d too large", C);
   const size_t total = static_cast<size_t>(HW) * (C / 4);
   int blocks = static_cast<int>((total + 256 * 8 - 1) / (256 * 8));
-  const int cap = (16 * num_sms() + B - 1) / B;
+  const int cap = (4 * num_sms() + B - 1) / B;   // one resident wave (4 CTAs x 256 threads x 64 registers per SM): the prologue is paid once
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   gn_apply_kernel<<<dim3(blocks, B), 256, 2 * C * sizeof(float), stream>>>(
