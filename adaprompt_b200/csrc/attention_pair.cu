@@ -29,7 +29,7 @@
 // af_attention_set_pair_variant(bit 0 = split, bit 1 = P in tensor memory, bit 2 = ping-pong exponentiation,
 // bit 3 = the row-split kernel further down, which is the default).
 #ifndef AF_ATTN_PAIR_VARIANT
-#define AF_ATTN_PAIR_VARIANT 2
+#define AF_ATTN_PAIR_VARIANT 8
 #endif
 
 // Every AF_ATTN_POLY_EVERY-th exponential of a row is evaluated on the FMA pipe (round-to-nearest split + degree-3
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(384, 1) attention_pair_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the tcgen05 issuers
 
   // register re-balancing (per warpgroup): the data-movement warpgroup keeps 40 registers per thread, the two
   // softmax warpgroups get 232 (a 128-wide fp32 score row lives in registers)
@@ -236,7 +236,9 @@ __global__ void __launch_bounds__(384, 1) attention_pair_kernel(const __grid_con
     // One issuing thread per query tile, each walking its own in-order chain S_{j+1}, PV_j with blocking mbarrier
     // waits (a single event-polling thread for both tiles added ~1000 cycles between "P_j written" and "PV_j
     // complete": profiles/r02_attention_pair.md).  K / V ring slots are released by the second of the two commits.
-    if (lane == 0) {
+    // The whole warp walks the chain (convergent, warp-uniform waits); one elected lane issues the tcgen05 instructions:
+    // under `if (lane == 0)` the compiler wraps every tcgen05.mma / commit in an elect - issue - branch loop.
+    {
       const int t = warp - 1;
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, DV);
@@ -245,14 +247,17 @@ __global__ void __launch_bounds__(384, 1) attention_pair_kernel(const __grid_con
       const uint32_t tm_s = tmem_base + kTmemS[t], tm_o = tmem_base + kTmemO[t], tm_p = tmem_base + kTmemP[t];
       auto issue_s = [&](int kslot) {   // S_t = Q_t . K^T for the K block at ring slot `kslot`
         const uint32_t k_addr = smem_u32(smem + S::kKOff + kslot * S::kKBytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < DK / 16; ++k) {
-          const uint64_t ad = umma_desc_sw128(q_addr + (k >> 2) * 128 * 128) + 2 * (k & 3);
-          const uint64_t bd = umma_desc_sw128(k_addr + (k >> 2) * BN * 128) + 2 * (k & 3);
-          tc_mma_ss(tm_s, ad, bd, idesc_s, k != 0 ? 1u : 0u);
+          for (int k = 0; k < DK / 16; ++k) {
+            const uint64_t ad = umma_desc_sw128(q_addr + (k >> 2) * 128 * 128) + 2 * (k & 3);
+            const uint64_t bd = umma_desc_sw128(k_addr + (k >> 2) * BN * 128) + 2 * (k & 3);
+            tc_mma_ss(tm_s, ad, bd, idesc_s, k != 0 ? 1u : 0u);
+          }
+          tc_commit(&s_full[t]);
+          tc_commit(&k_empty[kslot]);
         }
-        tc_commit(&s_full[t]);
-        tc_commit(&k_empty[kslot]);
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
@@ -276,21 +281,24 @@ __global__ void __launch_bounds__(384, 1) attention_pair_kernel(const __grid_con
           mbar_wait(&p_full[t * PA + hf], j & 1);
           tc_fence_after();
           stamp(2 + t, j, 2 + 2 * hf);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < HK / 16; ++kk) {
-            const int k = hf * (HK / 16) + kk;      // 16-key step within the block
-            const uint64_t bd = umma_desc_sw128(v_addr + (k >> 2) * S::kVAtomBytes) + 2 * (k & 3);
-            if constexpr (kPTmem) {
-              tc_mma_ts(tm_o, tm_p + k * 8, bd, idesc_o, (j | k) != 0 ? 1u : 0u);
-            } else {
-              const uint64_t ad = umma_desc_sw128(p_addr + (k >> 2) * 128 * 128) + 2 * (k & 3);
-              tc_mma_ss(tm_o, ad, bd, idesc_o, (j | k) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < HK / 16; ++kk) {
+              const int k = hf * (HK / 16) + kk;      // 16-key step within the block
+              const uint64_t bd = umma_desc_sw128(v_addr + (k >> 2) * S::kVAtomBytes) + 2 * (k & 3);
+              if constexpr (kPTmem) {
+                tc_mma_ts(tm_o, tm_p + k * 8, bd, idesc_o, (j | k) != 0 ? 1u : 0u);
+              } else {
+                const uint64_t ad = umma_desc_sw128(p_addr + (k >> 2) * 128 * 128) + 2 * (k & 3);
+                tc_mma_ss(tm_o, ad, bd, idesc_o, (j | k) != 0 ? 1u : 0u);
+              }
             }
+            tc_commit(&pv_done[t * PA + hf]);
+            if (hf == PA - 1) tc_commit(&v_empty[vslot]);
           }
-          tc_commit(&pv_done[t * PA + hf]);
+          __syncwarp();
           stamp(2 + t, j, 3 + 2 * hf);
         }
-        tc_commit(&v_empty[vslot]);
       }
     }
   }
@@ -560,7 +568,7 @@ __global__ void __launch_bounds__(640, 1) attention_rowsplit_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the tcgen05 issuers
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -595,7 +603,7 @@ __global__ void __launch_bounds__(640, 1) attention_rowsplit_kernel(const __grid
       }
     } else if (warp <= 2) {
       // ------------------------------------------------------------------ MMA issuer of tile t (in-order chain)
-      if (lane == 0) {
+      {   // whole warp, convergent; tcgen05 instructions by one elected lane (see attention_pair_kernel)
         const int t = warp - 1;
         constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN);
         constexpr uint32_t idesc_o = umma_idesc_bf16(128, DV);
@@ -603,14 +611,17 @@ __global__ void __launch_bounds__(640, 1) attention_rowsplit_kernel(const __grid
         const uint32_t tm_s = tmem_base + kTmemS[t], tm_o = tmem_base + kTmemO[t], tm_p = tmem_base + kTmemP[t];
         auto issue_s = [&](int kslot) {
           const uint32_t k_addr = smem_u32(smem + S::kKOff + kslot * S::kKBytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < DK / 16; ++k) {
-            const uint64_t ad = umma_desc_sw128(q_addr + (k >> 2) * 128 * 128) + 2 * (k & 3);
-            const uint64_t bd = umma_desc_sw128(k_addr + (k >> 2) * BN * 128) + 2 * (k & 3);
-            tc_mma_ss(tm_s, ad, bd, idesc_s, k != 0 ? 1u : 0u);
+            for (int k = 0; k < DK / 16; ++k) {
+              const uint64_t ad = umma_desc_sw128(q_addr + (k >> 2) * 128 * 128) + 2 * (k & 3);
+              const uint64_t bd = umma_desc_sw128(k_addr + (k >> 2) * BN * 128) + 2 * (k & 3);
+              tc_mma_ss(tm_s, ad, bd, idesc_s, k != 0 ? 1u : 0u);
+            }
+            tc_commit(&s_full[t]);
+            tc_commit(&k_empty[kslot]);
           }
-          tc_commit(&s_full[t]);
-          tc_commit(&k_empty[kslot]);
+          __syncwarp();
         };
         mbar_wait(q_full, 0);
         mbar_wait(&k_full[0], 0);
@@ -631,15 +642,18 @@ __global__ void __launch_bounds__(640, 1) attention_rowsplit_kernel(const __grid
           for (int hf = 0; hf < 2; ++hf) {
             mbar_wait(&p_full[t * 2 + hf], j & 1);
             tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < HC / 16; ++kk) {
-              const int k = hf * (HC / 16) + kk;
-              const uint64_t bd = umma_desc_sw128(v_addr + (k >> 2) * S::kVAtomBytes) + 2 * (k & 3);
-              tc_mma_ts(tm_o, tm_p + k * 8, bd, idesc_o, (j | k) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < HC / 16; ++kk) {
+                const int k = hf * (HC / 16) + kk;
+                const uint64_t bd = umma_desc_sw128(v_addr + (k >> 2) * S::kVAtomBytes) + 2 * (k & 3);
+                tc_mma_ts(tm_o, tm_p + k * 8, bd, idesc_o, (j | k) != 0 ? 1u : 0u);
+              }
+              tc_commit(&pv_done[t * 2 + hf]);
+              if (hf == 1) tc_commit(&v_empty[vslot]);
             }
-            tc_commit(&pv_done[t * 2 + hf]);
+            __syncwarp();
           }
-          tc_commit(&v_empty[vslot]);
         }
       }
     }

@@ -63,7 +63,8 @@ struct GemmParams {
 };
 
 constexpr int kEpiWarps = 8;                    // 2 warps per TMEM lane quarter, each takes every other 32-col chunk
-constexpr int kGemmThreads = 64 + kEpiWarps * 32;
+constexpr int kGemmThreads = 64 + kEpiWarps * 32 + 32;   // + the B-operand producer warp (last warp)
+constexpr int kBProducerWarp = 2 + kEpiWarps;
 constexpr int kSmemBudget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
 
 // SLOTS = per-warp ring of epilogue slots (32 rows x 128 B; 64 B rows for the bf16-only GEGLU output).  3 slots keep
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     tma_prefetch_desc(&p.tmOut);
     tma_prefetch_desc(&p.tmRes);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 2);     // A producer + B producer, each with its own expect_tx
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -178,61 +179,88 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   tc_fence_before();
   if constexpr (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // broadcast from lane 0: marks the address warp-uniform, so tcgen05 instructions take it from a uniform register
+  // instead of a per-instruction elect / R2UR.BROADCAST waterfall loop
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+  if (warp == 0 || warp == kBProducerWarp) {
+    // ------------------------------------------------------------------ TMA producers: warp 0 loads the A operand
+    // (activations / im2col taps), the last warp the B operand (weights).  One thread issuing both was a serial
+    // chain of ~520-780 cycles per ring stage (wait - expect_tx - two tensor-map loads) against 320 cycles of MMA
+    // work: the K-deep GEMMs / convolutions were producer bound (profiles/r01_gemm_epilogue_timeline.md).
+    const bool loads_a = warp == 0;
+    {   // whole warp, convergent: waits are warp-uniform, the TMA instructions are issued by one elected lane
       int stage = 0;
       uint32_t phase = 0;
+      constexpr uint32_t kATx = (CTA2 ? 2u : 1u) * Cfg::kABytes, kBTx = (CTA2 ? 2u : 1u) * Cfg::kBBytes;
       for (int tile = tile_first, tno = 0; tile < num_tiles; tile += tile_step, ++tno) {
         int n_tile, m_tile;
         tile_mn(tile, n_tile, m_tile);
-        stamp(0, tno, 0);
+        if (loads_a) stamp(0, tno, 0);
         const int n0 = n_tile * BN + (CTA2 ? static_cast<int>(cta_rank) * (BN / 2) : 0);
         int cw = 0, ch = 0, cn = 0;
-        if (p.amode != 0) {
+        if (loads_a && p.amode != 0) {
           cw = (m_tile % p.tiles_w) * p.bw;
           ch = ((m_tile / p.tiles_w) % p.tiles_h) * p.bh;
           cn = (m_tile / (p.tiles_w * p.tiles_h)) * p.nb;
         }
+        // (tap, channel block) of the K chunk are walked incrementally: no run-time integer division per stage
+        int cblk = 0, ky = 0, kx = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kTxBytes);
-          const int tap = kb / p.cpb;
-          const int cblk = kb - tap * p.cpb;
-          const bool second = cblk >= p.kb_split;
-          const CUtensorMap* tmA = second ? &p.tmA1 : &p.tmA0;
-          const int kc = (second ? cblk - p.kb_split : cblk) * 64;
-          const int ky = tap / 3, kx = tap - ky * 3;
-          // stride 2: input row 2*oh + ky - 1  ->  (coarse row oh + dh, parity ph)
-          const int ph = (ky == 1) ? 0 : 1, dh = (ky == 0) ? -1 : 0;
-          const int pw = (kx == 1) ? 0 : 1, dw = (kx == 0) ? -1 : 0;
-          if constexpr (CTA2) {
-            if (p.amode == 0) tma_load_2d_pair(sa, tmA, &full_bar[stage], kc, m_tile * 128);
-            else if (p.amode == 1) tma_load_4d_pair(sa, tmA, &full_bar[stage], kc, cw + kx - 1, ch + ky - 1, cn);
-            else tma_load_5d_pair(sa, tmA, &full_bar[stage], pw * p.C0 + kc, cw + dw, ph, ch + dh, cn);
-            tma_load_2d_pair(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
+          if (loads_a) {
+            const bool second = cblk >= p.kb_split;
+            const CUtensorMap* tmA = second ? &p.tmA1 : &p.tmA0;
+            const int kc = (second ? cblk - p.kb_split : cblk) * 64;
+            // stride 2: input row 2*oh + ky - 1  ->  (coarse row oh + dh, parity ph)
+            const int ph = (ky == 1) ? 0 : 1, dh = (ky == 0) ? -1 : 0;
+            const int pw = (kx == 1) ? 0 : 1, dw = (kx == 0) ? -1 : 0;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (elect_one()) {
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], kATx);
+              if constexpr (CTA2) {
+                if (p.amode == 0) tma_load_2d_pair(sa, tmA, &full_bar[stage], kc, m_tile * 128);
+                else if (p.amode == 1) tma_load_4d_pair(sa, tmA, &full_bar[stage], kc, cw + kx - 1, ch + ky - 1, cn);
+                else tma_load_5d_pair(sa, tmA, &full_bar[stage], pw * p.C0 + kc, cw + dw, ph, ch + dh, cn);
+              } else {
+                if (p.amode == 0) tma_load_2d(sa, tmA, &full_bar[stage], kc, m_tile * 128);
+                else if (p.amode == 1) tma_load_4d(sa, tmA, &full_bar[stage], kc, cw + kx - 1, ch + ky - 1, cn);
+                else tma_load_5d(sa, tmA, &full_bar[stage], pw * p.C0 + kc, cw + dw, ph, ch + dh, cn);
+              }
+            }
+            __syncwarp();
+            if (++cblk == p.cpb) {
+              cblk = 0;
+              if (++kx == 3) {
+                kx = 0;
+                ++ky;
+              }
+            }
           } else {
-            if (p.amode == 0) tma_load_2d(sa, tmA, &full_bar[stage], kc, m_tile * 128);
-            else if (p.amode == 1) tma_load_4d(sa, tmA, &full_bar[stage], kc, cw + kx - 1, ch + ky - 1, cn);
-            else tma_load_5d(sa, tmA, &full_bar[stage], pw * p.C0 + kc, cw + dw, ph, ch + dh, cn);
-            tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (elect_one()) {
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], kBTx);
+              if constexpr (CTA2) tma_load_2d_pair(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
+              else tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
+            }
+            __syncwarp();
           }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
-          if (kb == 0) stamp(0, tno, 1);
+          if (loads_a && kb == 0) stamp(0, tno, 1);
         }
-        stamp(0, tno, 2);
+        if (loads_a) stamp(0, tno, 2);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (pair: leader CTA only)
-    if (lane == 0 && leader) {
+    // The whole warp walks the loop (convergent control flow, warp-uniform barrier waits); the tcgen05 instructions are
+    // issued by one elected lane.  Under an `if (lane == 0)` branch the compiler wraps EVERY tcgen05.mma / commit in an
+    // elect - issue - branch waterfall loop, which cost ~50 cycles per instruction on this serial issue chain.
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 256 : 128, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -251,19 +279,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t adesc = umma_desc_sw128(sa);
           const uint64_t bdesc = umma_desc_sw128(sa + Cfg::kABytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // +32 bytes (16 bf16) along K inside the 128B swizzle atom == +2 in the >>4 address field
-            if constexpr (CTA2) tc_mma_ss2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else tc_mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              // +32 bytes (16 bf16) along K inside the 128B swizzle atom == +2 in the >>4 address field
+              if constexpr (CTA2) tc_mma_ss2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else tc_mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            if constexpr (CTA2) tc_commit2(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
           }
-          if constexpr (CTA2) tc_commit2(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        if constexpr (CTA2) tc_commit2(&tfull_bar[acc]); else tc_commit(&tfull_bar[acc]);
+        if (elect_one()) {
+          if constexpr (CTA2) tc_commit2(&tfull_bar[acc]); else tc_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
         stamp(1, tno, 3);
         if (++acc == 2) {
           acc = 0;
