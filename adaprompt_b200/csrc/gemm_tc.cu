@@ -350,9 +350,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         if (pf_tile < num_tiles) tile_rows(pf_tile, pf_n, pf_c1, pf_c2, pf_c3);
       }
     };
+    // All bulk-tensor instructions of this warp (residual loads, stores, group commits / waits) are issued by the lane
+    // `elect.sync` picks - the same lane every time for the full member mask, which the per-thread bulk async-groups
+    // need - instead of under `lane == 0`, where each of them was wrapped in an elect / branch waterfall loop.
     // residual prefetch distance: SLOTS - 1 items (SLOTS == 1: the next load waits for this item's store to drain)
     constexpr int kAhead = SLOTS > 1 ? SLOTS - 1 : 1;
-    if (has_res && lane == 0) {
+    if (has_res && elect_one()) {
 #pragma unroll
       for (int j = 0; j < kAhead; ++j) issue_res_load();
     }
@@ -415,7 +418,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           tmem_ld32(t_acc + BN / 2 + c, g);
           const int pc = n_tile * BN + c;                    // packed column of the value half (bias index)
           const bool col_ok = col0 < p.N / 2;                // N/2 is a multiple of 128: chunks are all-or-nothing
-          if (lane == 0) bulk_wait_read<SLOTS - 1>();        // the store that last used this slot has read it
+          if (elect_one()) bulk_wait_read<SLOTS - 1>();        // the store that last used this slot has read it
           __syncwarp();
           tmem_ld_wait();
           uint32_t pk[16];
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                 make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             tma_store_4d(&p.tmOut, slot, c0, c1, c2, c3);
             bulk_commit();
           }
@@ -460,7 +463,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           if (has_res) {
             mbar_wait(&my_res_bar[sl], (item / SLOTS) & 1);   // residual chunk landed in the slot
           } else {
-            if (lane == 0) bulk_wait_read<SLOTS - 1>();      // the store that last used this slot has read it
+            if (elect_one()) bulk_wait_read<SLOTS - 1>();      // the store that last used this slot has read it
             __syncwarp();
           }
           tmem_ld_wait();
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
               *reinterpret_cast<float2*>(p.gn_stats + (stat_slot * p.N + col0 + lane) * 2) = make_float2(s, ss);
           }
           if (ew == 0 && i == 0) stamp(2, tno, 3);
-          if (lane == 0) {
+          if (elect_one()) {
             if (col_ok) tma_store_4d(&p.tmOut, slot, c0, c1, c2, c3);
             bulk_commit();
             if (has_res) {
@@ -532,7 +535,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         acc_phase ^= 1;
       }
     }
-    if (lane == 0) bulk_wait_all();      // shared memory must outlive the bulk stores
+    if (elect_one()) bulk_wait_all();      // shared memory must outlive the bulk stores
   }
 
   tc_fence_before();
