@@ -124,35 +124,42 @@ __global__ void __launch_bounds__(320, 1) xattn_kernel(const __grid_constant__ X
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the tcgen05 issuer
 
   // 10 warps (no idle warps, no setmaxnreg): 65536 / 320 leaves 200 registers for the 80..128-wide score rows
   if (warp < 2) {
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer
-      if (lane == 0) {
-        mbar_arrive_expect_tx(kv_full, S::kKBytes + 2 * S::kVAtomBytes);
+      {   // whole warp, convergent; TMA instructions by one elected lane
+        if (elect_one()) {
+          mbar_arrive_expect_tx(kv_full, S::kKBytes + 2 * S::kVAtomBytes);
 #pragma unroll
-        for (int a = 0; a < KA; ++a)
-          tma_load_3d(smem + S::kKOff + a * 128 * 128, &p.tmK, kv_full, h * p.dp + a * 64, 0, b);
+          for (int a = 0; a < KA; ++a)
+            tma_load_3d(smem + S::kKOff + a * 128 * 128, &p.tmK, kv_full, h * p.dp + a * 64, 0, b);
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
-          tma_load_2d(smem + S::kVOff + a * S::kVAtomBytes, &p.tmV, kv_full, b * p.kv_stride + a * 64, h * p.d);
+          for (int a = 0; a < 2; ++a)
+            tma_load_2d(smem + S::kVOff + a * S::kVAtomBytes, &p.tmV, kv_full, b * p.kv_stride + a * 64, h * p.d);
+        }
+        __syncwarp();
         int slot = 0;
         uint32_t ph = 0;
         for (int i = 0; i < nt; ++i) {
           mbar_wait(&q_empty[slot], ph ^ 1);
-          mbar_arrive_expect_tx(&q_full[slot], S::kQBytes);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&q_full[slot], S::kQBytes);
 #pragma unroll
-          for (int a = 0; a < KA; ++a)
-            tma_load_3d(smem + S::kQOff + slot * S::kQBytes + a * 128 * 128, &p.tmQ, &q_full[slot],
-                        h * p.dp + a * 64, (tile0 + i) * 128, b);
+            for (int a = 0; a < KA; ++a)
+              tma_load_3d(smem + S::kQOff + slot * S::kQBytes + a * 128 * 128, &p.tmQ, &q_full[slot],
+                          h * p.dp + a * 64, (tile0 + i) * 128, b);
+          }
+          __syncwarp();
           if (++slot == QST) { slot = 0; ph ^= 1; }
         }
       }
     } else if (warp == 1) {
-      // ---------------------------------------------------------------- MMA issuer
-      if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer (whole warp, convergent; the
+      // tcgen05 instructions are issued by one elected lane: no per-instruction elect / branch waterfall loops)
+      {
         constexpr uint32_t idesc_s = umma_idesc_bf16(128, kcols16);
         constexpr uint32_t idesc_o = umma_idesc_bf16(128, DV);
         const uint32_t k_addr = smem_u32(smem + S::kKOff);
@@ -164,14 +171,17 @@ __global__ void __launch_bounds__(320, 1) xattn_kernel(const __grid_constant__ X
           mbar_wait(&q_full[slot], (i / QST) & 1);
           tc_fence_after();
           const uint32_t q_addr = smem_u32(smem + S::kQOff + slot * S::kQBytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < DK / 16; ++k) {
-            const uint64_t ad = umma_desc_sw128(q_addr + (k >> 2) * 128 * 128) + 2 * (k & 3);
-            const uint64_t bd = umma_desc_sw128(k_addr + (k >> 2) * 128 * 128) + 2 * (k & 3);
-            tc_mma_ss(tmem_base + kTmemS[i & 1], ad, bd, idesc_s, k != 0 ? 1u : 0u);
+            for (int k = 0; k < DK / 16; ++k) {
+              const uint64_t ad = umma_desc_sw128(q_addr + (k >> 2) * 128 * 128) + 2 * (k & 3);
+              const uint64_t bd = umma_desc_sw128(k_addr + (k >> 2) * 128 * 128) + 2 * (k & 3);
+              tc_mma_ss(tmem_base + kTmemS[i & 1], ad, bd, idesc_s, k != 0 ? 1u : 0u);
+            }
+            tc_commit(&s_full[i & 1]);
+            tc_commit(&q_empty[slot]);
           }
-          tc_commit(&s_full[i & 1]);
-          tc_commit(&q_empty[slot]);
+          __syncwarp();
         };
         mbar_wait(kv_full, 0);
         issue_s(0);
@@ -180,13 +190,16 @@ __global__ void __launch_bounds__(320, 1) xattn_kernel(const __grid_constant__ X
           const int w = i & 1;
           mbar_wait(&p_full[w], (i >> 1) & 1);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = umma_desc_sw128(p_addr + w * S::kPBytes + (k >> 2) * 128 * 128) + 2 * (k & 3);
-            const uint64_t bd = umma_desc_sw128(v_addr + (k >> 2) * S::kVAtomBytes) + 2 * (k & 3);
-            tc_mma_ss(tmem_base + kTmemO[w], ad, bd, idesc_o, k != 0 ? 1u : 0u);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ad = umma_desc_sw128(p_addr + w * S::kPBytes + (k >> 2) * 128 * 128) + 2 * (k & 3);
+              const uint64_t bd = umma_desc_sw128(v_addr + (k >> 2) * S::kVAtomBytes) + 2 * (k & 3);
+              tc_mma_ss(tmem_base + kTmemO[w], ad, bd, idesc_o, k != 0 ? 1u : 0u);
+            }
+            tc_commit(&pv_done[w]);
           }
-          tc_commit(&pv_done[w]);
+          __syncwarp();
           if (i + 2 < nt) issue_s(i + 2);
         }
       }
