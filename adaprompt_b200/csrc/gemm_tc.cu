@@ -272,9 +272,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         tc_fence_after();
         stamp(1, tno, 1);
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
+        long long waited = 0;       // timeline probe only: cycles this tile's K loop spent waiting for operands
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          const long long w0 = tracing ? clock64() : 0;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (tracing) waited += clock64() - w0;
           if (kb == 0) stamp(1, tno, 2);
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t adesc = umma_desc_sw128(sa);
@@ -299,6 +302,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         }
         __syncwarp();
         stamp(1, tno, 3);
+        if (tracing && tno < 32) p.trace[(1 * 32 + tno) * 8 + 4] = waited;
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

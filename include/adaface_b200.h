@@ -76,7 +76,7 @@ int af_gemm_set_pair_mode(int mode);
  * device_buffer (>= 3*32*8 int64, caller-owned) CTA 0 of every following launch records clock64 stamps
  * [actor: TMA producer, MMA issuer, epilogue warp 0][its first 32 tiles][8 events]
  * (producer: tile begin, first stage issued, last stage issued; MMA: begin, accumulator free, first stage landed, tile
- * committed; epilogue: tile begin, accumulator full, first chunk in registers, first chunk in smem, first store issued,
+ * committed, cycles of the K loop spent waiting for operands; epilogue: tile begin, accumulator full, first chunk in registers, first chunk in smem, first store issued,
  * tile done).  Null switches it off. */
 int af_gemm_set_trace(long long* device_buffer);
 

@@ -41,4 +41,5 @@ if valid:
     mm = t[1]
     print("MMA issuer, mean cycles: wait acc free", st.mean([int(mm[i, 1] - mm[i, 0]) for i in valid]),
           "| wait first stage", st.mean([int(mm[i, 2] - mm[i, 1]) for i in valid]),
-          "| k loop", st.mean([int(mm[i, 3] - mm[i, 2]) for i in valid]))
+          "| k loop", st.mean([int(mm[i, 3] - mm[i, 2]) for i in valid]),
+          "of which waiting for operands", st.mean([int(mm[i, 4]) for i in valid]))
