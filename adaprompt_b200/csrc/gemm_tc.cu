@@ -464,8 +464,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
               b4[j].x += rb.x; b4[j].y += rb.y; b4[j].z += rb.z; b4[j].w += rb.w;
             }
           }
+          if (ew == 0 && i == 0) stamp(2, tno, 6);
           if (has_res) {
             mbar_wait(&my_res_bar[sl], (item / SLOTS) & 1);   // residual chunk landed in the slot
+            if (ew == 0 && i == 0) stamp(2, tno, 7);
           } else {
             if (elect_one()) bulk_wait_read<SLOTS - 1>();      // the store that last used this slot has read it
             __syncwarp();

@@ -37,6 +37,9 @@ if valid:
           "| first chunk: ld", st.mean([int(ep[i, 2] - ep[i, 1]) for i in valid]),
           "math+sts", st.mean([int(ep[i, 3] - ep[i, 2]) for i in valid]),
           "store+next", st.mean([int(ep[i, 4] - ep[i, 3]) for i in valid]),
+          "(ld split: issue+bias", st.mean([int(ep[i, 6] - ep[i, 1]) for i in valid]),
+          "residual wait", st.mean([int(ep[i, 7] - ep[i, 6]) for i in valid]) if res else 0,
+          "tmem wait", st.mean([int(ep[i, 2] - (ep[i, 7] if res else ep[i, 6])) for i in valid]), ")",
           "| rest of tile", st.mean([int(ep[i, 5] - ep[i, 4]) for i in valid]))
     mm = t[1]
     print("MMA issuer, mean cycles: wait acc free", st.mean([int(mm[i, 1] - mm[i, 0]) for i in valid]),
