@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(192, 1) attention_kernel(const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the tcgen05 issuer
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -179,8 +179,9 @@ __global__ void __launch_bounds__(192, 1) attention_kernel(const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, convergent; the tcgen05
+    // instructions are issued by one elected lane instead of under `lane == 0`: no per-instruction waterfall loops)
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, DV);
       const uint32_t q_addr = smem_u32(smem + S::kQOff);
@@ -192,14 +193,17 @@ __global__ void __launch_bounds__(192, 1) attention_kernel(const __grid_constant
         tc_fence_after();
         const uint32_t k_addr = smem_u32(smem + S::kKOff + ks * S::kKBytes);
         const uint32_t d_tmem = tmem_base + ((j & 1) ? kTmemS1 : kTmemS0);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < DK / 16; ++k) {
-          const uint64_t ad = umma_desc_sw128(q_addr + (k >> 2) * 128 * 128) + 2 * (k & 3);
-          const uint64_t bd = umma_desc_sw128(k_addr + (k >> 2) * BN * 128) + 2 * (k & 3);
-          tc_mma_ss(d_tmem, ad, bd, idesc_s, k != 0 ? 1u : 0u);
+          for (int k = 0; k < DK / 16; ++k) {
+            const uint64_t ad = umma_desc_sw128(q_addr + (k >> 2) * 128 * 128) + 2 * (k & 3);
+            const uint64_t bd = umma_desc_sw128(k_addr + (k >> 2) * BN * 128) + 2 * (k & 3);
+            tc_mma_ss(d_tmem, ad, bd, idesc_s, k != 0 ? 1u : 0u);
+          }
+          tc_commit(&k_empty[ks]);
+          tc_commit(&s_full[j & 1]);
         }
-        tc_commit(&k_empty[ks]);
-        tc_commit(&s_full[j & 1]);
+        __syncwarp();
         if (++ks == C::KSTAGES) { ks = 0; kph ^= 1; }
       };
       mbar_wait(q_full, 0);
@@ -211,14 +215,17 @@ __global__ void __launch_bounds__(192, 1) attention_kernel(const __grid_constant
         pph ^= 1;
         tc_fence_after();
         const uint32_t v_addr = smem_u32(smem + S::kVOff + vs * S::kVBytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BN / 16; ++k) {
-          const uint64_t ad = umma_desc_sw128(p_addr + (k >> 2) * 128 * 128) + 2 * (k & 3);
-          const uint64_t bd = umma_desc_sw128(v_addr + (k >> 2) * S::kVAtomBytes) + 2 * (k & 3);
-          tc_mma_ss(tmem_base + kTmemO, ad, bd, idesc_o, (j | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BN / 16; ++k) {
+            const uint64_t ad = umma_desc_sw128(p_addr + (k >> 2) * 128 * 128) + 2 * (k & 3);
+            const uint64_t bd = umma_desc_sw128(v_addr + (k >> 2) * S::kVAtomBytes) + 2 * (k & 3);
+            tc_mma_ss(tmem_base + kTmemO, ad, bd, idesc_o, (j | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&v_empty[vs]);
+          tc_commit(pv_done);
         }
-        tc_commit(&v_empty[vs]);
-        tc_commit(pv_done);
+        __syncwarp();
         if (++vs == C::VSTAGES) { vs = 0; vph ^= 1; }
       }
     }
