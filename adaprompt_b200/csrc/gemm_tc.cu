@@ -452,7 +452,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           }
         } else {
           uint32_t v[32];
+          if (ew == 0 && i == 0) stamp(3, tno, 0);
           tmem_ld32(t_acc + c, v);
+          if (ew == 0 && i == 0) stamp(3, tno, 1);
           const bool col_ok = col0 < p.N;
           float4 b4[8];
 #pragma unroll
@@ -488,6 +490,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             }
             o[j] = t4;
           }
+          if (ew == 0 && i == 0) stamp(3, tno, 2);
           if (p.out_bf16) {
             if (has_res) __syncwarp();                       // every lane has read its residual row
 #pragma unroll
@@ -500,7 +503,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             for (int j = 0; j < 8; ++j)
               *reinterpret_cast<float4*>(slot + lane * 128 + ((j ^ (lane & 7)) << 4)) = o[j];
           }
+          if (ew == 0 && i == 0) stamp(3, tno, 3);
           fence_async_smem();
+          if (ew == 0 && i == 0) stamp(3, tno, 4);
           __syncwarp();
           if (p.gn_stats && !p.out_bf16) {
             // per-channel (sum, sum of squares) over this warp's valid rows: lane = column, fixed row order

@@ -73,7 +73,7 @@ int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* A1, long lo
  * Results are bit-identical between the modes (same accumulation order). */
 int af_gemm_set_pair_mode(int mode);
 /* Timeline probe of af_gemm_bf16 / af_conv3x3_bf16 (measurement aid, results unaffected): with a non-null
- * device_buffer (>= 3*32*8 int64, caller-owned) CTA 0 of every following launch records clock64 stamps
+ * device_buffer (>= 4*32*8 int64, caller-owned; the 4th actor holds extra epilogue stamps) CTA 0 of every following launch records clock64 stamps
  * [actor: TMA producer, MMA issuer, epilogue warp 0][its first 32 tiles][8 events]
  * (producer: tile begin, first stage issued, last stage issued; MMA: begin, accumulator free, first stage landed, tile
  * committed, cycles of the K loop spent waiting for operands; epilogue: tile begin, accumulator full, first chunk in registers, first chunk in smem, first store issued,

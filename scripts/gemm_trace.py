@@ -18,9 +18,9 @@ e0.record()
 for _ in range(10): f()
 e1.record(); torch.cuda.synchronize()
 print(f"M{M} N{N} K{K} res={res} f32={f32}: {e0.elapsed_time(e1) * 100:.1f} us per launch")
-buf = torch.zeros(3 * 32 * 8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(4 * 32 * 8, dtype=torch.int64, device="cuda")
 lib.af_gemm_set_trace(buf.data_ptr()); f(); torch.cuda.synchronize(); lib.af_gemm_set_trace(None)
-t = buf.cpu().view(3, 32, 8)
+t = buf.cpu().view(4, 32, 8)
 t0 = int(t[t > 0].min())
 names = (("prod", 3), ("mma", 4), ("epi", 6))
 for tile in range(8):
@@ -41,6 +41,14 @@ if valid:
           "residual wait", st.mean([int(ep[i, 7] - ep[i, 6]) for i in valid]) if res else 0,
           "tmem wait", st.mean([int(ep[i, 2] - (ep[i, 7] if res else ep[i, 6])) for i in valid]), ")",
           "| rest of tile", st.mean([int(ep[i, 5] - ep[i, 4]) for i in valid]))
+    x = t[3]
+    print("first chunk detail: before ld issue", st.mean([int(x[i, 0] - ep[i, 1]) for i in valid]),
+          "| ld issue", st.mean([int(x[i, 1] - x[i, 0]) for i in valid]),
+          "| bias loads", st.mean([int(ep[i, 6] - x[i, 1]) for i in valid]),
+          "| math (tmem wait -> o[] ready)", st.mean([int(x[i, 2] - ep[i, 2]) for i in valid]),
+          "| st.shared", st.mean([int(x[i, 3] - x[i, 2]) for i in valid]),
+          "| fence.proxy.async", st.mean([int(x[i, 4] - x[i, 3]) for i in valid]),
+          "| syncwarp(+stats)", st.mean([int(ep[i, 3] - x[i, 4]) for i in valid]))
     mm = t[1]
     print("MMA issuer, mean cycles: wait acc free", st.mean([int(mm[i, 1] - mm[i, 0]) for i in valid]),
           "| wait first stage", st.mean([int(mm[i, 2] - mm[i, 1]) for i in valid]),
