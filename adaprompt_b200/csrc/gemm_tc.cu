@@ -413,6 +413,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         const int col0 = n_tile * kOutCols + c;              // first output column
         const int sl = item % SLOTS;
         uint8_t* slot = my_slots + sl * Cfg::kSlotBytes;
+        const uint32_t slot_a = smem_u32(slot);           // shared-space address: LDS / STS, not generic LD.E / ST.E
         const int c0 = col0;
 
         if constexpr (GEGLU) {
@@ -442,8 +443,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(slot + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
-                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            sts128(slot_a + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           fence_async_smem();
           __syncwarp();
           if (elect_one()) {
@@ -458,12 +458,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           const bool col_ok = col0 < p.N;
           float4 b4[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias && col0 + 4 * j < p.N) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
-            if (rb_row && col0 + 4 * j < p.N) {
-              const float4 rb = __ldg(reinterpret_cast<const float4*>(rb_row + col0) + j);
-              b4[j].x += rb.x; b4[j].y += rb.y; b4[j].z += rb.z; b4[j].w += rb.w;
+          for (int j = 0; j < 8; ++j) b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const bool full_chunk = col0 + 32 <= p.N;     // uniform; partial chunks only at the right edge of N
+          if (p.bias) {
+            if (full_chunk) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (col0 + 4 * j < p.N) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+            }
+          }
+          if (rb_row) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (full_chunk || col0 + 4 * j < p.N) {
+                const float4 rb = __ldg(reinterpret_cast<const float4*>(rb_row + col0) + j);
+                b4[j].x += rb.x; b4[j].y += rb.y; b4[j].z += rb.z; b4[j].w += rb.w;
+              }
             }
           }
           if (ew == 0 && i == 0) stamp(2, tno, 6);
@@ -476,32 +489,39 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           }
           tmem_ld_wait();
           if (ew == 0 && i == 0) stamp(2, tno, 2);
+          // one uniform branch per OPTION, not per element group: with the activation / residual tests inside the
+          // unrolled loop the compiler kept 16 taken branches per item (~70 cycles each on this serial chain)
           float4 o[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 t4 = make_float4(__uint_as_float(v[4 * j]) + b4[j].x, __uint_as_float(v[4 * j + 1]) + b4[j].y,
-                                    __uint_as_float(v[4 * j + 2]) + b4[j].z, __uint_as_float(v[4 * j + 3]) + b4[j].w);
-            if (p.act == 1) {
-              t4.x = quick_gelu(t4.x); t4.y = quick_gelu(t4.y); t4.z = quick_gelu(t4.z); t4.w = quick_gelu(t4.w);
+          for (int j = 0; j < 8; ++j)
+            o[j] = make_float4(__uint_as_float(v[4 * j]) + b4[j].x, __uint_as_float(v[4 * j + 1]) + b4[j].y,
+                               __uint_as_float(v[4 * j + 2]) + b4[j].z, __uint_as_float(v[4 * j + 3]) + b4[j].w);
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              o[j].x = quick_gelu(o[j].x); o[j].y = quick_gelu(o[j].y);
+              o[j].z = quick_gelu(o[j].z); o[j].w = quick_gelu(o[j].w);
             }
-            if (has_res) {
-              const float4 r4 = *reinterpret_cast<const float4*>(slot + lane * 128 + ((j ^ (lane & 7)) << 4));
-              t4.x += r4.x; t4.y += r4.y; t4.z += r4.z; t4.w += r4.w;
+          }
+          if (has_res) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 r4 = lds128f(slot_a + lane * 128 + ((j ^ (lane & 7)) << 4));
+              o[j].x += r4.x; o[j].y += r4.y; o[j].z += r4.z; o[j].w += r4.w;
             }
-            o[j] = t4;
           }
           if (ew == 0 && i == 0) stamp(3, tno, 2);
           if (p.out_bf16) {
             if (has_res) __syncwarp();                       // every lane has read its residual row
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(slot + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
-                  make_uint4(pack_bf16x2(o[2 * j].x, o[2 * j].y), pack_bf16x2(o[2 * j].z, o[2 * j].w),
-                             pack_bf16x2(o[2 * j + 1].x, o[2 * j + 1].y), pack_bf16x2(o[2 * j + 1].z, o[2 * j + 1].w));
+              sts128(slot_a + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), pack_bf16x2(o[2 * j].x, o[2 * j].y),
+                     pack_bf16x2(o[2 * j].z, o[2 * j].w), pack_bf16x2(o[2 * j + 1].x, o[2 * j + 1].y),
+                     pack_bf16x2(o[2 * j + 1].z, o[2 * j + 1].w));
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(slot + lane * 128 + ((j ^ (lane & 7)) << 4)) = o[j];
+              sts128f(slot_a + lane * 128 + ((j ^ (lane & 7)) << 4), o[j]);
           }
           if (ew == 0 && i == 0) stamp(3, tno, 3);
           fence_async_smem();
@@ -513,7 +533,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll 8
             for (int r = 0; r < 32; ++r) {
               if ((row_mask >> r) & 1u) {
-                const float x = *reinterpret_cast<const float*>(slot + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
+                const float x = lds32f(slot_a + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
                 s += x;
                 ss = fmaf(x, x, ss);
               }
