@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(192, 1) attention_kernel(const __grid_constant
         pk.w = pack_bf16x2(pe[6], pe[7]);
         uint8_t* atom = p_row + (c8 >> 6) * (128 * 128);
         const uint32_t chunk = static_cast<uint32_t>((c8 & 63) >> 3);  // 16-byte chunk inside the 128-byte row
-        *reinterpret_cast<uint4*>(atom + ((chunk ^ sw) << 4)) = pk;
+        sts128(smem_u32(atom) + ((chunk ^ sw) << 4), pk.x, pk.y, pk.z, pk.w);   // STS, not a generic ST.E
       }
       l_run = l_run * alpha + ((l4[0] + l4[1]) + (l4[2] + l4[3]));
       m_run = m_new;

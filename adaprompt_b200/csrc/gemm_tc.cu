@@ -427,13 +427,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           __syncwarp();
           tmem_ld_wait();
           uint32_t pk[16];
+          float4 bvs[8], bgs[8];                             // bias rows of the value / gate halves: ONE option test
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bvs[j] = bgs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias && col_ok) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              bvs[j] = __ldg(reinterpret_cast<const float4*>(p.bias + pc) + j);
+              bgs[j] = __ldg(reinterpret_cast<const float4*>(p.bias + pc + BN / 2) + j);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
-            if (p.bias && col_ok) {
-              bv = __ldg(reinterpret_cast<const float4*>(p.bias + pc) + j);
-              bg = __ldg(reinterpret_cast<const float4*>(p.bias + pc + BN / 2) + j);
-            }
+            const float4 bv = bvs[j], bg = bgs[j];
             const float o0 = (__uint_as_float(v[4 * j + 0]) + bv.x) * gelu_tanh(__uint_as_float(g[4 * j + 0]) + bg.x);
             const float o1 = (__uint_as_float(v[4 * j + 1]) + bv.y) * gelu_tanh(__uint_as_float(g[4 * j + 1]) + bg.y);
             const float o2 = (__uint_as_float(v[4 * j + 2]) + bv.z) * gelu_tanh(__uint_as_float(g[4 * j + 2]) + bg.z);

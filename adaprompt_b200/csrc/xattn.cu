@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(320, 1) xattn_kernel(const __grid_constant__ X
             pk.w = pack_bf16x2(pe[6], pe[7]);
             uint8_t* atom = p_row + (c8 >> 6) * (128 * 128);
             const uint32_t chunk = static_cast<uint32_t>((c8 & 63) >> 3);
-            *reinterpret_cast<uint4*>(atom + ((chunk ^ sw) << 4)) = pk;
+            sts128(smem_u32(atom) + ((chunk ^ sw) << 4), pk.x, pk.y, pk.z, pk.w);   // STS, not a generic ST.E
       }
       const float l_run = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       fence_async_smem();
