@@ -25,6 +25,8 @@
 // smem ring of kStages {A 128x64, B BNx64} 128B-swizzled tiles; 2 TMEM accumulator stages so the
 // epilogue of tile i overlaps the mainloop of tile i+1.
 #include "../../include/adaface_b200.h"
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace af {
@@ -204,59 +206,75 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           ch = ((m_tile / p.tiles_w) % p.tiles_h) * p.bh;
           cn = (m_tile / (p.tiles_w * p.tiles_h)) * p.nb;
         }
-        // (tap, channel block) of the K chunk are walked incrementally: no run-time integer division per stage
-        int cblk = 0, ky = 0, kx = 0;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
-          if (loads_a) {
-            const bool second = cblk >= p.kb_split;
-            const CUtensorMap* tmA = second ? &p.tmA1 : &p.tmA0;
-            const int kc = (second ? cblk - p.kb_split : cblk) * 64;
-            // stride 2: input row 2*oh + ky - 1  ->  (coarse row oh + dh, parity ph)
-            const int ph = (ky == 1) ? 0 : 1, dh = (ky == 0) ? -1 : 0;
-            const int pw = (kx == 1) ? 0 : 1, dw = (kx == 0) ? -1 : 0;
+        // (tap, channel block) of the K chunk are walked incrementally: no run-time integer division per stage.  The
+        // operand mode is a compile-time constant inside each loop instance (generic lambda + integral_constant): the
+        // per-stage chain of the producer has no option branches left.
+        auto a_loop = [&](auto amode_c) {
+          constexpr int AM = decltype(amode_c)::value;
+          int cblk = 0, ky = 0, kx = 0;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            const bool second = AM == 0 && cblk >= p.kb_split;     // dual-source K only exists for linear GEMMs ...
+            const bool second_c = AM == 1 && cblk >= p.kb_split;   // ... and stride-1 convolutions (concat input)
+            const CUtensorMap* tmA = (second || second_c) ? &p.tmA1 : &p.tmA0;
+            const int kc = ((second || second_c) ? cblk - p.kb_split : cblk) * 64;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (elect_one()) {
               if (leader) mbar_arrive_expect_tx(&full_bar[stage], kATx);
-              if constexpr (CTA2) {
-                if (p.amode == 0) tma_load_2d_pair(sa, tmA, &full_bar[stage], kc, m_tile * 128);
-                else if (p.amode == 1) tma_load_4d_pair(sa, tmA, &full_bar[stage], kc, cw + kx - 1, ch + ky - 1, cn);
-                else tma_load_5d_pair(sa, tmA, &full_bar[stage], pw * p.C0 + kc, cw + dw, ph, ch + dh, cn);
+              if constexpr (AM == 0) {
+                if constexpr (CTA2) tma_load_2d_pair(sa, tmA, &full_bar[stage], kc, m_tile * 128);
+                else tma_load_2d(sa, tmA, &full_bar[stage], kc, m_tile * 128);
+              } else if constexpr (AM == 1) {
+                if constexpr (CTA2) tma_load_4d_pair(sa, tmA, &full_bar[stage], kc, cw + kx - 1, ch + ky - 1, cn);
+                else tma_load_4d(sa, tmA, &full_bar[stage], kc, cw + kx - 1, ch + ky - 1, cn);
               } else {
-                if (p.amode == 0) tma_load_2d(sa, tmA, &full_bar[stage], kc, m_tile * 128);
-                else if (p.amode == 1) tma_load_4d(sa, tmA, &full_bar[stage], kc, cw + kx - 1, ch + ky - 1, cn);
+                // stride 2: input row 2*oh + ky - 1  ->  (coarse row oh + dh, parity ph)
+                const int ph = (ky == 1) ? 0 : 1, dh = (ky == 0) ? -1 : 0;
+                const int pw = (kx == 1) ? 0 : 1, dw = (kx == 0) ? -1 : 0;
+                if constexpr (CTA2) tma_load_5d_pair(sa, tmA, &full_bar[stage], pw * p.C0 + kc, cw + dw, ph, ch + dh, cn);
                 else tma_load_5d(sa, tmA, &full_bar[stage], pw * p.C0 + kc, cw + dw, ph, ch + dh, cn);
               }
             }
-            __syncwarp();
-            if (++cblk == p.cpb) {
+            if (AM != 0 && ++cblk == p.cpb) {
               cblk = 0;
               if (++kx == 3) {
                 kx = 0;
                 ++ky;
               }
             }
-          } else {
+            if (AM == 0) ++cblk;
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            if (kb == 0) stamp(0, tno, 1);
+          }
+        };
+        if (loads_a) {
+          if (p.amode == 0) a_loop(std::integral_constant<int, 0>{});
+          else if (p.amode == 1) a_loop(std::integral_constant<int, 1>{});
+          else a_loop(std::integral_constant<int, 2>{});
+        } else {
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            uint8_t* sb = smem + stage * Cfg::kStageBytes + Cfg::kABytes;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (elect_one()) {
               if (leader) mbar_arrive_expect_tx(&full_bar[stage], kBTx);
               if constexpr (CTA2) tma_load_2d_pair(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
               else tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * 64, n0);
             }
-            __syncwarp();
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
-          if (loads_a && kb == 0) stamp(0, tno, 1);
         }
         if (loads_a) stamp(0, tno, 2);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (pair: leader CTA only)
+    // (No __syncwarp after the elected sections: the next elect.sync / warp-uniform wait reconverges the warp.)
     // The whole warp walks the loop (convergent control flow, warp-uniform barrier waits); the tcgen05 instructions are
     // issued by one elected lane.  Under an `if (lane == 0)` branch the compiler wraps EVERY tcgen05.mma / commit in an
     // elect - issue - branch waterfall loop, which cost ~50 cycles per instruction on this serial issue chain.
@@ -291,7 +309,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             }
             if constexpr (CTA2) tc_commit2(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
           }
-          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -300,7 +317,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         if (elect_one()) {
           if constexpr (CTA2) tc_commit2(&tfull_bar[acc]); else tc_commit(&tfull_bar[acc]);
         }
-        __syncwarp();
         stamp(1, tno, 3);
         if (tracing && tno < 32) p.trace[(1 * 32 + tno) * 8 + 4] = waited;
         if (++acc == 2) {
