@@ -51,3 +51,16 @@ if case == "all":
     gemm_case(8192, 8192, 8192, False, False, bn=128)
     conv_case(16, 64, 320, 320)
     conv_case(16, 8, 1280, 1280)
+if case == "bn":
+    for bn in (0, 128):
+        gemm_case(65536, 320, 320, True, True, bn=bn)
+        gemm_case(65536, 320, 320, False, True, bn=bn)
+        gemm_case(65536, 320, 320, False, False, bn=bn)
+        gemm_case(16384, 640, 640, True, True, bn=bn)
+        gemm_case(16384, 640, 640, False, False, bn=bn)
+        gemm_case(4096, 1280, 1280, True, True, bn=bn)
+        gemm_case(65536, 768, 320, False, False, bn=bn)
+        gemm_case(65536, 384, 320, False, False, bn=bn)
+        gemm_case(16384, 1280, 640, False, False, bn=bn)
+        gemm_case(4096, 2560, 1280, False, False, bn=bn)
+        gemm_case(320, 65536, 320, False, False, bn=bn)
