@@ -27,29 +27,84 @@ __device__ __forceinline__ float gn_dxhat(float xhat, float dy, float g, float b
   return dy * g;
 }
 
+// grid = (chunks, B); block = 256.  Thread t owns channel quad (t % cq) and pixel lane (t / cq) of the chunk's rows:
+// 16-byte x loads and 8-byte dy loads, four rows in flight per thread, lanes folded through shared memory in a fixed
+// order (bit-reproducible).  (The first version walked one channel per thread with scalar loads in a serial row loop:
+// 155 us per call on average, 11 % of the stage-1 step.)
 __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                              const float* __restrict__ mean_rstd,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              int C, int HW, int rows_per_chunk, int silu,
                                                              float* __restrict__ partial) {
+  extern __shared__ float s_part[];   // [lanes][cq][8]
   const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
   const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
-  const int cpg = C / 32;
-  for (int c = threadIdx.x; c < C; c += 256) {
-    const int g = c / cpg;
-    const float mean = mean_rstd[(b * 32 + g) * 2], rstd = mean_rstd[(b * 32 + g) * 2 + 1];
-    const float ga = gamma[c], be = beta[c];
-    float s1 = 0.f, s2 = 0.f;
-    for (int r = r0; r < r1; ++r) {
-      const size_t i = (static_cast<size_t>(b) * HW + r) * C + c;
-      const float xh = (x[i] - mean) * rstd;
-      const float d = gn_dxhat(xh, bf(dy[i]), ga, be, silu);
-      s1 += d;
-      s2 += d * xh;
+  const int cpg = C / 32, cq = C >> 2;
+  const int lanes = cq <= 256 ? 256 / cq : 1;
+  auto accumulate = [&](int q, int r_first, int r_step, int dst) {
+    const int c = q * 4;
+    float mean[4], rstd[4], ga[4], be[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int g = (c + e) / cpg;
+      mean[e] = mean_rstd[(b * 32 + g) * 2];
+      rstd[e] = mean_rstd[(b * 32 + g) * 2 + 1];
+      ga[e] = gamma[c + e];
+      be[e] = beta[c + e];
     }
-    float* o = partial + ((static_cast<size_t>(b) * chunks + chunk) * C + c) * 2;
-    o[0] = s1;
-    o[1] = s2;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    const size_t base = static_cast<size_t>(b) * HW * C + c;
+    auto acc = [&](const float4& xv, const uint2& dv) {
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      const __nv_bfloat162 d01 = *reinterpret_cast<const __nv_bfloat162*>(&dv.x);
+      const __nv_bfloat162 d23 = *reinterpret_cast<const __nv_bfloat162*>(&dv.y);
+      const float ds[4] = {__low2float(d01), __high2float(d01), __low2float(d23), __high2float(d23)};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float xh = (xs[e] - mean[e]) * rstd[e];
+        const float d = gn_dxhat(xh, ds[e], ga[e], be[e], silu);
+        s1[e] += d;
+        s2[e] = fmaf(d, xh, s2[e]);
+      }
+    };
+    int r = r_first;
+    for (; r + 3 * r_step < r1; r += 4 * r_step) {
+      float4 xv[4];
+      uint2 dv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const size_t i = base + static_cast<size_t>(r + u * r_step) * C;
+        xv[u] = __ldg(reinterpret_cast<const float4*>(x + i));
+        dv[u] = __ldg(reinterpret_cast<const uint2*>(dy + i));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc(xv[u], dv[u]);
+    }
+    for (; r < r1; r += r_step) {
+      const size_t i = base + static_cast<size_t>(r) * C;
+      acc(__ldg(reinterpret_cast<const float4*>(x + i)), __ldg(reinterpret_cast<const uint2*>(dy + i)));
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      s_part[dst * 8 + 2 * e] = s1[e];
+      s_part[dst * 8 + 2 * e + 1] = s2[e];
+    }
+  };
+  if (cq <= 256) {
+    if (threadIdx.x < lanes * cq) accumulate(threadIdx.x % cq, r0 + threadIdx.x / cq, lanes, threadIdx.x);
+  } else {
+    for (int q = threadIdx.x; q < cq; q += 256) accumulate(q, r0, 1, q);
+  }
+  __syncthreads();
+  float* out = partial + (static_cast<size_t>(b) * chunks + chunk) * C * 2;
+  for (int q = threadIdx.x; q < cq; q += 256) {
+    float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int l = 0; l < lanes; ++l)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t[e] += s_part[(l * cq + q) * 8 + e];
+    float4* o = reinterpret_cast<float4*>(out + q * 8);
+    o[0] = make_float4(t[0], t[1], t[2], t[3]);
+    o[1] = make_float4(t[4], t[5], t[6], t[7]);
   }
 }
 
@@ -78,6 +133,7 @@ __global__ void __launch_bounds__(128) gn_bwd_finalize_kernel(const float* __res
   }
 }
 
+// grid = (blocks, B); block = 256: channel quads, 16-byte loads / stores, channel index tracked incrementally
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                            const float* __restrict__ mean_rstd, const float* __restrict__ sums,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -86,23 +142,46 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const float* __restri
   const int b = blockIdx.y;
   const int cpg = C / 32;
   const float inv_n = 1.0f / (static_cast<float>(HW) * cpg);
-  __shared__ float tab[32][4];
-  if (threadIdx.x < 32) {
-    tab[threadIdx.x][0] = mean_rstd[(b * 32 + threadIdx.x) * 2];
-    tab[threadIdx.x][1] = mean_rstd[(b * 32 + threadIdx.x) * 2 + 1];
-    tab[threadIdx.x][2] = sums[(b * 32 + threadIdx.x) * 2] * inv_n;
-    tab[threadIdx.x][3] = sums[(b * 32 + threadIdx.x) * 2 + 1] * inv_n;
+  extern __shared__ float s_tab[];          // [C][6]: mean, rstd, m1, m2, gamma, beta per channel
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int g = c / cpg;
+    s_tab[c * 6 + 0] = mean_rstd[(b * 32 + g) * 2];
+    s_tab[c * 6 + 1] = mean_rstd[(b * 32 + g) * 2 + 1];
+    s_tab[c * 6 + 2] = sums[(b * 32 + g) * 2] * inv_n;
+    s_tab[c * 6 + 3] = sums[(b * 32 + g) * 2 + 1] * inv_n;
+    s_tab[c * 6 + 4] = gamma[c];
+    s_tab[c * 6 + 5] = beta[c];
   }
   __syncthreads();
-  const size_t n = static_cast<size_t>(HW) * C;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * 256) {
-    const int c = static_cast<int>(i % C), g = c / cpg;
-    const size_t k = static_cast<size_t>(b) * n + i;
-    const float xh = (x[k] - tab[g][0]) * tab[g][1];
-    const float d = gn_dxhat(xh, bf(dy[k]), gamma[c], beta[c], silu);
-    float v = tab[g][1] * (d - tab[g][2] - xh * tab[g][3]);
-    if (dres) v += dres[k];
-    dx[k] = v;
+  const uint32_t cq = static_cast<uint32_t>(C >> 2);
+  const uint32_t total = static_cast<uint32_t>(HW) * cq;
+  const uint32_t step = gridDim.x * 256u;
+  const uint32_t step_q = step % cq;
+  uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  uint32_t q = i % cq;
+  const size_t sample = static_cast<size_t>(b) * HW * C;
+  for (; i < total; i += step) {
+    const size_t k = sample + static_cast<size_t>(i) * 4;
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + k));
+    const uint2 dv = __ldg(reinterpret_cast<const uint2*>(dy + k));
+    float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dres) rv = __ldg(reinterpret_cast<const float4*>(dres + k));
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    const __nv_bfloat162 d01 = *reinterpret_cast<const __nv_bfloat162*>(&dv.x);
+    const __nv_bfloat162 d23 = *reinterpret_cast<const __nv_bfloat162*>(&dv.y);
+    const float ds[4] = {__low2float(d01), __high2float(d01), __low2float(d23), __high2float(d23)};
+    const float rs[4] = {rv.x, rv.y, rv.z, rv.w};
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float* t = s_tab + (q * 4 + e) * 6;
+      const float xh = (xs[e] - t[0]) * t[1];
+      const float d = gn_dxhat(xh, ds[e], t[4], t[5], silu);
+      o[e] = t[1] * (d - t[2] - xh * t[3]) + rs[e];
+    }
+    *reinterpret_cast<float4*>(dx + k) = make_float4(o[0], o[1], o[2], o[3]);
+    q += step_q;
+    if (q >= cq) q -= cq;
   }
 }
 
@@ -452,9 +531,17 @@ static inline unsigned grid_for(size_t n) {
 
 using namespace af;
 
+static int gn_bwd_chunks(int B, int HW) {
+  int chunks = (4 * num_sms() + B - 1) / B;      // fill the machine ...
+  if (chunks > HW / 16) chunks = HW / 16;        // ... with at least 16 rows per block
+  if (chunks > 256) chunks = 256;
+  if (chunks < 1) chunks = 1;
+  return chunks;
+}
+
 extern "C" size_t af_groupnorm_bwd_workspace_floats(int B, int C, int HW) {
-  int chunks = (HW + 63) / 64;
-  if (chunks > 64) chunks = 64;
+  (void)HW;
+  const int chunks = 256;                        // upper bound of gn_bwd_chunks
   return static_cast<size_t>(B) * chunks * C * 2 + static_cast<size_t>(B) * 64;
 }
 
@@ -462,22 +549,31 @@ extern "C" int af_groupnorm_bwd(const float* x, int C, int B, int HW, const floa
                                 const float* beta, int silu, const void* dy_bf16, const float* dres, float* dx,
                                 float* workspace, cudaStream_t stream) {
   AF_CHECK_ARG(x && mean_rstd && gamma && beta && dy_bf16 && dx && workspace, "af_groupnorm_bwd: null pointer");
-  AF_CHECK_ARG(C > 0 && C % 32 == 0 && B > 0 && HW > 0, "af_groupnorm_bwd: bad sizes");
-  int chunks = (HW + 63) / 64;
-  if (chunks > 64) chunks = 64;
+  AF_CHECK_ARG(C > 0 && C % 32 == 0 && B > 0 && HW > 0 && C <= 5120, "af_groupnorm_bwd: bad sizes");
+  AF_CHECK_ARG(static_cast<long long>(HW) * (C / 4) < (1ll << 31), "af_groupnorm_bwd: sample too large for 32-bit quad indices");
+  const int chunks = gn_bwd_chunks(B, HW);
   const int rows_per_chunk = (HW + chunks - 1) / chunks;
   float* partial = workspace;
   float* sums = workspace + static_cast<size_t>(B) * chunks * C * 2;
   const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(dy_bf16);
-  gn_bwd_partial_kernel<<<dim3(chunks, B), 256, 0, stream>>>(x, dy, mean_rstd, gamma, beta, C, HW, rows_per_chunk, silu, partial);
+  const int cq = C / 4;
+  const size_t smem_p = static_cast<size_t>(cq <= 256 ? (256 / cq) * cq : cq) * 8 * sizeof(float);
+  gn_bwd_partial_kernel<<<dim3(chunks, B), 256, smem_p, stream>>>(x, dy, mean_rstd, gamma, beta, C, HW, rows_per_chunk, silu, partial);
   AF_LAUNCH_CHECK("gn_bwd_partial_kernel");
   gn_bwd_finalize_kernel<<<B * 32, 128, 0, stream>>>(partial, C, chunks, sums);
   AF_LAUNCH_CHECK("gn_bwd_finalize_kernel");
-  const size_t n = static_cast<size_t>(HW) * C;
-  unsigned gx = static_cast<unsigned>((n + 255) / 256);
+  const size_t nq = static_cast<size_t>(HW) * cq;
+  unsigned gx = static_cast<unsigned>((nq + 256 * 4 - 1) / (256 * 4));
   const unsigned cap = static_cast<unsigned>(num_sms() * 8 / B + 1);
   if (gx > cap) gx = cap;
-  gn_bwd_apply_kernel<<<dim3(gx, B), 256, 0, stream>>>(x, dy, mean_rstd, sums, gamma, beta, dres, C, HW, silu, dx);
+  if (gx < 1) gx = 1;
+  const size_t smem_a = static_cast<size_t>(C) * 6 * sizeof(float);
+  static size_t configured = 0;
+  if (smem_a > 48 * 1024 && smem_a > configured) {
+    AF_CUDA(cudaFuncSetAttribute(gn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_a)));
+    configured = smem_a;
+  }
+  gn_bwd_apply_kernel<<<dim3(gx, B), 256, smem_a, stream>>>(x, dy, mean_rstd, sums, gamma, beta, dres, C, HW, silu, dx);
   AF_LAUNCH_CHECK("gn_bwd_apply_kernel");
   return 0;
 }

@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--bs", type=int, default=4)
     ap.add_argument("--accum", type=int, default=2)
     ap.add_argument("--latent", type=int, default=64)
+    ap.add_argument("--breakdown", action="store_true", help="per-entry-point CUDA-event times of one optimizer step (stderr)")
     args = ap.parse_args()
     import torch.distributed as dist
     from adaprompt_b200 import _lib
@@ -112,6 +113,16 @@ def main():
     for _ in range(args.warmup):
         loss, gn = optimizer_step()
     torch.cuda.synchronize()
+    if args.breakdown and rank == 0:
+        with _lib.profile() as prof:
+            optimizer_step()
+        summ = prof.summary()
+        tot = sum(v["ms"] for v in summ.values())
+        print(f"one optimizer step: {sum(v['launches'] for v in summ.values())} C-ABI calls, {tot:.1f} ms of kernel time", file=sys.stderr)
+        for n, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])[:16]:
+            print(f"  {n:28s} x{v['launches']:5d} {v['ms']:8.2f} ms  {v['flops'] / max(v['ms'], 1e-9) / 1e9:7.1f} TFLOP/s", file=sys.stderr)
+        for n, v in sorted(prof.by_shape.items(), key=lambda kv: -kv[1]["ms"])[:24]:
+            print(f"    {n:60s} x{v['launches']:4d} {v['ms']:8.2f} ms", file=sys.stderr)
     if world > 1:
         dist.barrier()
     n0 = _lib.TRACE.count
