@@ -200,6 +200,9 @@ def _sig(name, a):
         ep = a[9]._obj
         return f"M{a[7]} N{a[8]} K{a[2] + a[5]}{' geglu' if ep.geglu else ''}{' res' if ep.residual else ''}" \
                f"{' f32' if ep.out_dtype == 0 else ''}"
+    if name == "af_bgemm_bf16":
+        g = a[0]._obj
+        return f"M{g.M} N{g.N} K{g.K} nb{g.nb0}x{g.nb1} mode{g.mode}"
     if name == "af_conv3x3_bf16":
         return f"B{a[5]} {a[6]}x{a[7]} C{a[1] + a[3]}->{a[8]} s{a[9]}"
     if name == "af_attention_bf16":

@@ -50,7 +50,9 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 
 constexpr int kBM = 128, kBK = 32, kPitch = kBK + 8, kStages = 3;
 
-template <int BN>
+// MODE is a template parameter: as a run-time field the epilogue carried a five-way option chain inside its 32-iteration
+// element loop (the same pattern that cost the tcgen05 GEMM epilogue 70 cycles per iteration).
+template <int BN, int MODE>
 __global__ void __launch_bounds__(256) bgemm_kernel(const BgemmParams p) {
   constexpr int WARPS_N = BN / 32, WARPS_M = 8 / WARPS_N, WM = kBM / WARPS_M, MT = WM / 16;
   extern __shared__ __align__(16) uint8_t smem_b[];
@@ -126,22 +128,22 @@ __global__ void __launch_bounds__(256) bgemm_kernel(const BgemmParams p) {
     for (int hrow = 0; hrow < 2; ++hrow) {
       const int row = m0 + wm * WM + i * 16 + (lane >> 2) + hrow * 8;
       if (row >= p.M) continue;
-      const float rv = (vec && (p.mode == 1 || p.mode == 3) && row < p.valid_rows) ? vec[row] : 0.f;
+      const float rv = (vec && (MODE == 1 || MODE == 3) && row < p.valid_rows) ? vec[row] : 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int col = n0 + wn * 32 + j * 8 + (lane & 3) * 2;
         if (col >= p.N) continue;
         float v0 = acc[i][j][hrow * 2], v1 = acc[i][j][hrow * 2 + 1];
         const bool ok0 = row < p.valid_rows && col < p.valid_cols, ok1 = row < p.valid_rows && col + 1 < p.valid_cols;
-        if (p.mode == 0) {
+        if constexpr (MODE == 0) {
           v0 *= p.alpha; v1 *= p.alpha;
-        } else if (p.mode == 1) {
+        } else if constexpr (MODE == 1) {
           v0 = fast_exp2(v0 - rv); v1 = fast_exp2(v1 - rv);
-        } else if (p.mode == 2) {
+        } else if constexpr (MODE == 2) {
           v0 = fast_exp2(v0 - (ok0 ? vec[col] : 0.f)); v1 = fast_exp2(v1 - (ok1 ? vec[col + 1] : 0.f));
         } else {
           const __nv_bfloat162 pp = *reinterpret_cast<const __nv_bfloat162*>(P + static_cast<long long>(row) * p.ldp + col);
-          const float c0 = p.mode == 3 ? rv : (ok0 ? vec[col] : 0.f), c1 = p.mode == 3 ? rv : (ok1 ? vec[col + 1] : 0.f);
+          const float c0 = MODE == 3 ? rv : (ok0 ? vec[col] : 0.f), c1 = MODE == 3 ? rv : (ok1 ? vec[col + 1] : 0.f);
           v0 = p.alpha * __bfloat162float(pp.x) * (v0 - c0);
           v1 = p.alpha * __bfloat162float(pp.y) * (v1 - c1);
         }
@@ -156,18 +158,28 @@ __global__ void __launch_bounds__(256) bgemm_kernel(const BgemmParams p) {
     }
 }
 
-template <int BN>
-static int launch_bgemm(const BgemmParams& p, int batch, cudaStream_t stream) {
+template <int BN, int MODE>
+static int launch_bgemm_m(const BgemmParams& p, int batch, cudaStream_t stream) {
   constexpr int smem = kStages * (kBM + BN) * kPitch * 2;
   static bool configured = false;
   if (!configured) {
-    AF_CUDA(cudaFuncSetAttribute(bgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AF_CUDA(cudaFuncSetAttribute(bgemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, batch);
-  bgemm_kernel<BN><<<grid, 256, smem, stream>>>(p);
+  bgemm_kernel<BN, MODE><<<grid, 256, smem, stream>>>(p);
   AF_LAUNCH_CHECK("bgemm_kernel");
   return 0;
+}
+template <int BN>
+static int launch_bgemm(const BgemmParams& p, int batch, cudaStream_t stream) {
+  switch (p.mode) {
+    case 0: return launch_bgemm_m<BN, 0>(p, batch, stream);
+    case 1: return launch_bgemm_m<BN, 1>(p, batch, stream);
+    case 2: return launch_bgemm_m<BN, 2>(p, batch, stream);
+    case 3: return launch_bgemm_m<BN, 3>(p, batch, stream);
+    default: return launch_bgemm_m<BN, 4>(p, batch, stream);
+  }
 }
 
 }  // namespace af
