@@ -24,7 +24,7 @@ struct BgemmParams {
   void* C; long long ldc, sC0, sC1; int c_f32;
   const float* vec; long long sV0, sV1;
   const __nv_bfloat16* P; long long ldp, sP0, sP1;
-  int M, N, K, nb1, mode, valid_rows, valid_cols;
+  int M, N, K, nb1, mode, valid_rows, valid_cols, staged;
   float alpha;
 };
 
@@ -64,6 +64,22 @@ __global__ void __launch_bounds__(256) bgemm_kernel(const BgemmParams p) {
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
   const __nv_bfloat16* A = p.A + b0 * p.sA0 + b1 * p.sA1;
   const __nv_bfloat16* B = p.B + b0 * p.sB0 + b1 * p.sB1;
+  // Staged epilogue (bf16 outputs with 16-byte aligned rows): the tile is converted into shared memory and leaves in
+  // 16-byte row chunks; for modes 3 / 4 the P tile is fetched the same way by cp.async BEFORE the main loop.  (With one
+  // 4-byte store / load per accumulator pair the 4096 x 4096 softmax-recompute GEMMs ran at 1.1 TB/s.)
+  constexpr int kCP = BN + 8;                                                  // staging pitch (bf16 elements)
+  __nv_bfloat16* sC = reinterpret_cast<__nv_bfloat16*>(smem_b);                // reuses the operand ring after the loop
+  __nv_bfloat16* sP = sB + kStages * BN * kPitch;                              // [128][kCP], modes 3 / 4 only
+  const bool staged = p.staged != 0;
+  const __nv_bfloat16* Pt = p.P ? p.P + b0 * p.sP0 + b1 * p.sP1 : nullptr;
+  if (MODE >= 3 && staged) {
+    for (int i = tid; i < kBM * (BN / 8); i += 256) {
+      const int r = i / (BN / 8), c = (i % (BN / 8)) * 8;
+      const bool ok = (m0 + r) < p.M && (n0 + c) < p.N;                       // N % 8 == 0 when staged
+      cp_async16(sP + r * kCP + c, ok ? Pt + static_cast<long long>(m0 + r) * p.ldp + n0 + c : Pt, ok);
+    }
+    cp_async_commit();
+  }
 
   auto load_stage = [&](int stage, int k0) {
     __nv_bfloat16* a = sA + stage * kBM * kPitch;
@@ -120,18 +136,21 @@ __global__ void __launch_bounds__(256) bgemm_kernel(const BgemmParams p) {
 
   // ---- epilogue
   const float* vec = p.vec ? p.vec + b0 * p.sV0 + b1 * p.sV1 : nullptr;
-  const __nv_bfloat16* P = p.P ? p.P + b0 * p.sP0 + b1 * p.sP1 : nullptr;
+  const __nv_bfloat16* P = Pt;
   uint8_t* Cb = static_cast<uint8_t*>(p.C) + (b0 * p.sC0 + b1 * p.sC1) * (p.c_f32 ? 4 : 2);
+  if (staged) __syncthreads();          // every warp is done with the operand ring (sC aliases it); sP has landed
 #pragma unroll
   for (int i = 0; i < MT; ++i)
 #pragma unroll
     for (int hrow = 0; hrow < 2; ++hrow) {
-      const int row = m0 + wm * WM + i * 16 + (lane >> 2) + hrow * 8;
+      const int lrow = wm * WM + i * 16 + (lane >> 2) + hrow * 8;
+      const int row = m0 + lrow;
       if (row >= p.M) continue;
       const float rv = (vec && (MODE == 1 || MODE == 3) && row < p.valid_rows) ? vec[row] : 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int col = n0 + wn * 32 + j * 8 + (lane & 3) * 2;
+        const int lcol = wn * 32 + j * 8 + (lane & 3) * 2;
+        const int col = n0 + lcol;
         if (col >= p.N) continue;
         float v0 = acc[i][j][hrow * 2], v1 = acc[i][j][hrow * 2 + 1];
         const bool ok0 = row < p.valid_rows && col < p.valid_cols, ok1 = row < p.valid_rows && col + 1 < p.valid_cols;
@@ -142,25 +161,40 @@ __global__ void __launch_bounds__(256) bgemm_kernel(const BgemmParams p) {
         } else if constexpr (MODE == 2) {
           v0 = fast_exp2(v0 - (ok0 ? vec[col] : 0.f)); v1 = fast_exp2(v1 - (ok1 ? vec[col + 1] : 0.f));
         } else {
-          const __nv_bfloat162 pp = *reinterpret_cast<const __nv_bfloat162*>(P + static_cast<long long>(row) * p.ldp + col);
+          const __nv_bfloat162 pp = staged ? *reinterpret_cast<const __nv_bfloat162*>(sP + lrow * kCP + lcol)
+                                           : *reinterpret_cast<const __nv_bfloat162*>(P + static_cast<long long>(row) * p.ldp + col);
           const float c0 = MODE == 3 ? rv : (ok0 ? vec[col] : 0.f), c1 = MODE == 3 ? rv : (ok1 ? vec[col + 1] : 0.f);
           v0 = p.alpha * __bfloat162float(pp.x) * (v0 - c0);
           v1 = p.alpha * __bfloat162float(pp.y) * (v1 - c1);
         }
         v0 = ok0 ? v0 : 0.f;
         v1 = ok1 ? v1 : 0.f;
-        if (p.c_f32) {
+        if (staged) {
+          *reinterpret_cast<uint32_t*>(sC + lrow * kCP + lcol) = pack_bf16x2(v0, v1);
+        } else if (p.c_f32) {
           *reinterpret_cast<float2*>(reinterpret_cast<float*>(Cb) + static_cast<long long>(row) * p.ldc + col) = make_float2(v0, v1);
         } else {
           *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(Cb) + static_cast<long long>(row) * p.ldc + col) = pack_bf16x2(v0, v1);
         }
       }
     }
+  if (staged) {
+    __syncthreads();
+    __nv_bfloat16* Cg = reinterpret_cast<__nv_bfloat16*>(Cb);
+    for (int i = tid; i < kBM * (BN / 8); i += 256) {
+      const int r = i / (BN / 8), c = (i % (BN / 8)) * 8;
+      if (m0 + r < p.M && n0 + c < p.N)
+        *reinterpret_cast<uint4*>(Cg + static_cast<long long>(m0 + r) * p.ldc + n0 + c) =
+            *reinterpret_cast<const uint4*>(sC + r * kCP + c);
+    }
+  }
 }
 
 template <int BN, int MODE>
 static int launch_bgemm_m(const BgemmParams& p, int batch, cudaStream_t stream) {
-  constexpr int smem = kStages * (kBM + BN) * kPitch * 2;
+  // operand ring (also the output staging tile: 128 x (BN + 8) bf16 fits) + the P tile of modes 3 / 4
+  static_assert(kStages * (kBM + BN) * kPitch >= kBM * (BN + 8), "staging tile must fit in the operand ring");
+  constexpr int smem = kStages * (kBM + BN) * kPitch * 2 + (MODE >= 3 ? kBM * (BN + 8) * 2 : 0);
   static bool configured = false;
   if (!configured) {
     AF_CUDA(cudaFuncSetAttribute(bgemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -209,6 +243,11 @@ extern "C" int af_bgemm_bf16(const af_bgemm* g, cudaStream_t stream) {
   p.valid_rows = g->valid_rows > 0 ? g->valid_rows : g->M;
   p.valid_cols = g->valid_cols > 0 ? g->valid_cols : g->N;
   p.alpha = g->alpha;
+  // staged (coalesced) epilogue: bf16 output whose rows and batch slices start on 16-byte boundaries
+  p.staged = (!p.c_f32 && g->mode != 0 && g->N % 8 == 0 && g->ldc % 8 == 0 && g->sC0 % 8 == 0 && g->sC1 % 8 == 0 &&
+              (reinterpret_cast<uintptr_t>(g->C) & 15) == 0 &&
+              (g->mode < 3 || (g->ldp % 8 == 0 && g->sP0 % 8 == 0 && g->sP1 % 8 == 0 &&
+                               (reinterpret_cast<uintptr_t>(g->P) & 15) == 0))) ? 1 : 0;
   const int batch = g->nb0 * g->nb1;
   return g->N <= 64 ? launch_bgemm<64>(p, batch, stream) : launch_bgemm<128>(p, batch, stream);
 }
