@@ -43,18 +43,33 @@ __global__ void __launch_bounds__(256) attention_small_kernel(const __nv_bfloat1
   }
   __syncthreads();
   float* pw = sp + warp * nk;
-  for (int i = warp; i < L; i += nwarps) {
+  float* sq = sp + nwarps * nk + warp * kTD;       // this warp's query row (scaled)
+  // queries are split over the warps of the block AND over gridDim.z blocks (each block stages K / V of its head again:
+  // 40 KB from L2); scores: one KEY per lane and 64 FMAs per key - the first version put the 64 channels on the lanes
+  // and paid a 5-step shuffle reduction per (query, key) pair, 68 us for a 77-token layer
+  for (int i = blockIdx.z * nwarps + warp; i < L; i += nwarps * gridDim.z) {
     const __nv_bfloat16* qrow = qkv + (static_cast<size_t>(b) * L + i) * ldq + h * kTD;
-    const float q0 = __bfloat162float(qrow[lane]) * scale, q1 = __bfloat162float(qrow[lane + 32]) * scale;
+    sq[lane] = __bfloat162float(qrow[lane]) * scale;
+    sq[lane + 32] = __bfloat162float(qrow[lane + 32]) * scale;
+    __syncwarp();
     const int kmax = causal ? (i + 1) * mult : nk;
     float mx = -INFINITY;
-    for (int j = 0; j < kmax; ++j) {   // dot(q, k_j): lanes over the 64 channels, warp-reduced
-      float d = q0 * sk[j * (kTD + 1) + lane] + q1 * sk[j * (kTD + 1) + lane + 32];
-      d = warp_sum(d);
-      if (lane == 0) pw[j] = d;
+    for (int j = lane; j < kmax; j += 32) {
+      const float* kr = sk + j * (kTD + 1);
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < kTD; c += 4) {
+        d0 = fmaf(sq[c], kr[c], d0);
+        d1 = fmaf(sq[c + 1], kr[c + 1], d1);
+        d2 = fmaf(sq[c + 2], kr[c + 2], d2);
+        d3 = fmaf(sq[c + 3], kr[c + 3], d3);
+      }
+      const float d = (d0 + d1) + (d2 + d3);
+      pw[j] = d;
       mx = fmaxf(mx, d);
     }
-    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float sum = 0.f;
     for (int j = lane; j < kmax; j += 32) {
       const float e = __expf(pw[j] - mx);
@@ -175,7 +190,7 @@ extern "C" int af_attention_small(const void* qkv, long long ldq, int k_off, int
   AF_CHECK_ARG(qkv && out, "af_attention_small: null pointer");
   AF_CHECK_ARG(B > 0 && heads > 0 && L > 0 && mult >= 1, "af_attention_small: bad sizes");
   const int nk = L * mult;
-  const size_t smem = (static_cast<size_t>(nk) * (kTD + 1) + static_cast<size_t>(nk) * kTD + 8 * nk) * sizeof(float);
+  const size_t smem = (static_cast<size_t>(nk) * (kTD + 1) + static_cast<size_t>(nk) * kTD + 8 * nk + 8 * kTD) * sizeof(float);
   AF_CHECK_ARG(smem <= 200 * 1024, "af_attention_small: L*mult=%d too large", nk);
   static size_t configured = 0;
   if (smem > configured) {
@@ -183,7 +198,10 @@ extern "C" int af_attention_small(const void* qkv, long long ldq, int k_off, int
                                  static_cast<int>(smem)));
     configured = smem;
   }
-  attention_small_kernel<<<dim3(heads, B), 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ldq, k_off, v_off,
+  int qsplit = (2 * num_sms()) / (heads * B);       // fill the machine: heads x B blocks alone leave most SMs idle
+  if (qsplit > (L + 7) / 8) qsplit = (L + 7) / 8;
+  if (qsplit < 1) qsplit = 1;
+  attention_small_kernel<<<dim3(heads, B, qsplit), 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ldq, k_off, v_off,
                                                                 L, mult, heads, scale, causal,
                                                                 static_cast<__nv_bfloat16*>(out), ldo);
   AF_LAUNCH_CHECK("attention_small_kernel");
