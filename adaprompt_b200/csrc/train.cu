@@ -328,9 +328,11 @@ __global__ void __launch_bounds__(256) attention_small_bwd_kernel(const __nv_bfl
   const int Lk = L * mult;
   float* Q = sm;                 // [L][64]
   float* dO = Q + L * 64;        // [L][64]
-  float* K = dO + L * 64;        // [Lk][64]
-  float* V = K + Lk * 64;        // [Lk][64]
-  float* P = V + Lk * 64;        // [L][Lk]
+  // K / V rows are padded to 65 floats: the score loop below walks them with one KEY per thread (stride-64 rows put all
+  // 32 lanes on one bank: the kernel took 146 us for a 77-token layer)
+  float* K = dO + L * 64;        // [Lk][65]
+  float* V = K + Lk * 65;        // [Lk][65]
+  float* P = V + Lk * 65;        // [L][Lk]
   float* dS = P + L * Lk;        // [L][Lk]
   const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * L * ldq;
   for (int i = threadIdx.x; i < L * 64; i += 256) {
@@ -340,8 +342,8 @@ __global__ void __launch_bounds__(256) attention_small_bwd_kernel(const __nv_bfl
   }
   for (int i = threadIdx.x; i < Lk * 64; i += 256) {
     const int j = i >> 6, c = i & 63, t = j / mult, r = j % mult;
-    K[i] = bf(base[t * ldq + k_off + (h * mult + r) * 64 + c]);
-    V[i] = bf(base[t * ldq + v_off + (h * mult + r) * 64 + c]);
+    K[j * 65 + c] = bf(base[t * ldq + k_off + (h * mult + r) * 64 + c]);
+    V[j * 65 + c] = bf(base[t * ldq + v_off + (h * mult + r) * 64 + c]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < L * Lk; i += 256) {
@@ -350,8 +352,8 @@ __global__ void __launch_bounds__(256) attention_small_bwd_kernel(const __nv_bfl
     if (!causal || j / mult <= q) {
       s = 0.f;
       for (int c = 0; c < 64; ++c) {
-        s += Q[q * 64 + c] * K[j * 64 + c];
-        dp += dO[q * 64 + c] * V[j * 64 + c];
+        s += Q[q * 64 + c] * K[j * 65 + c];
+        dp += dO[q * 64 + c] * V[j * 65 + c];
       }
     }
     P[i] = s;
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(256) attention_small_bwd_kernel(const __nv_bfl
   for (int i = threadIdx.x; i < L * 64; i += 256) {    // dQ (carries the forward scale)
     const int q = i >> 6, c = i & 63;
     float s = 0.f;
-    for (int j = 0; j < Lk; ++j) s += dS[q * Lk + j] * K[j * 64 + c];
+    for (int j = 0; j < Lk; ++j) s += dS[q * Lk + j] * K[j * 65 + c];
     obase[q * ldq + h * 64 + c] = __float2bfloat16(s * scale);
   }
   for (int i = threadIdx.x; i < Lk * 64; i += 256) {   // dK, dV
@@ -639,7 +641,7 @@ extern "C" int af_attention_small_bwd(const void* qkv, long long ldq, int k_off,
                                       cudaStream_t stream) {
   AF_CHECK_ARG(qkv && dout && dqkv && B > 0 && heads > 0 && L > 0 && mult >= 1, "af_attention_small_bwd: bad arguments");
   const int Lk = L * mult;
-  const size_t smem = (static_cast<size_t>(2) * L * 64 + static_cast<size_t>(2) * Lk * 64 + static_cast<size_t>(2) * L * Lk) * 4;
+  const size_t smem = (static_cast<size_t>(2) * L * 64 + static_cast<size_t>(2) * Lk * 65 + static_cast<size_t>(2) * L * Lk) * 4;
   AF_CHECK_ARG(smem <= 227 * 1024, "af_attention_small_bwd: L=%d mult=%d needs %zu bytes of shared memory", L, mult, smem);
   AF_CUDA(cudaFuncSetAttribute(attention_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   attention_small_bwd_kernel<<<B * heads, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ldq, k_off, v_off,
