@@ -64,3 +64,8 @@ if case == "bn":
         gemm_case(16384, 1280, 640, False, False, bn=bn)
         gemm_case(4096, 2560, 1280, False, False, bn=bn)
         gemm_case(320, 65536, 320, False, False, bn=bn)
+if case == "vt":
+    for bn in (128, 160, 256):
+        gemm_case(320, 65536, 320, False, False, bn=bn)
+        gemm_case(640, 16384, 640, False, False, bn=bn)
+        gemm_case(1280, 4096, 1280, False, False, bn=bn)
