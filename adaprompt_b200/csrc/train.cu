@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256) rowdot_heads_kernel(const __nv_bfloat16* 
 // CLIP text attention backward (forward: text.cu attention_small_kernel; adaface/arc2face_models.py:87-173).
 // One CTA per (sample, head); everything in shared memory in fp32.  Lk = L * mult keys, key j = (token j / mult ... see
 // layout note) - key (t, r) lives in row t of qkv at column k_off + (h*mult + r)*64 and is visible to query i iff t <= i.
-__global__ void __launch_bounds__(256) attention_small_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ldq, int k_off,
+__global__ void __launch_bounds__(1024) attention_small_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ldq, int k_off,
                                                                   int v_off, const __nv_bfloat16* __restrict__ dout, long long ldo,
                                                                   __nv_bfloat16* __restrict__ dqkv, int heads, int L, int mult,
                                                                   float scale, int causal) {
@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(256) attention_small_bwd_kernel(const __nv_bfl
   const int Lk = L * mult;
   float* Q = sm;                 // [L][64]
   float* dO = Q + L * 64;        // [L][64]
+  // (1024 threads per (sample, head): only B x heads blocks exist and every phase is a block-wide strided loop)
   // K / V rows are padded to 65 floats: the score loop below walks them with one KEY per thread (stride-64 rows put all
   // 32 lanes on one bank: the kernel took 146 us for a 77-token layer)
   float* K = dO + L * 64;        // [Lk][65]
@@ -335,18 +336,18 @@ __global__ void __launch_bounds__(256) attention_small_bwd_kernel(const __nv_bfl
   float* P = V + Lk * 65;        // [L][Lk]
   float* dS = P + L * Lk;        // [L][Lk]
   const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * L * ldq;
-  for (int i = threadIdx.x; i < L * 64; i += 256) {
+  for (int i = threadIdx.x; i < L * 64; i += blockDim.x) {
     const int t = i >> 6, c = i & 63;
     Q[i] = bf(base[t * ldq + h * 64 + c]) * scale;
     dO[i] = bf(dout[(static_cast<size_t>(b) * L + t) * ldo + h * 64 + c]);
   }
-  for (int i = threadIdx.x; i < Lk * 64; i += 256) {
+  for (int i = threadIdx.x; i < Lk * 64; i += blockDim.x) {
     const int j = i >> 6, c = i & 63, t = j / mult, r = j % mult;
     K[j * 65 + c] = bf(base[t * ldq + k_off + (h * mult + r) * 64 + c]);
     V[j * 65 + c] = bf(base[t * ldq + v_off + (h * mult + r) * 64 + c]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < L * Lk; i += 256) {
+  for (int i = threadIdx.x; i < L * Lk; i += blockDim.x) {
     const int q = i / Lk, j = i % Lk;
     float s = -INFINITY, dp = 0.f;
     if (!causal || j / mult <= q) {
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(256) attention_small_bwd_kernel(const __nv_bfl
     dS[i] = dp;
   }
   __syncthreads();
-  for (int q = threadIdx.x >> 5; q < L; q += 8) {     // one warp per row: softmax, delta, dS
+  for (int q = threadIdx.x >> 5; q < L; q += (blockDim.x >> 5)) {     // one warp per row: softmax, delta, dS
     const int lane = threadIdx.x & 31;
     float m = -INFINITY;
     for (int j = lane; j < Lk; j += 32) m = fmaxf(m, P[q * Lk + j]);
@@ -384,13 +385,13 @@ __global__ void __launch_bounds__(256) attention_small_bwd_kernel(const __nv_bfl
   }
   __syncthreads();
   __nv_bfloat16* obase = dqkv + static_cast<size_t>(b) * L * ldq;
-  for (int i = threadIdx.x; i < L * 64; i += 256) {    // dQ (carries the forward scale)
+  for (int i = threadIdx.x; i < L * 64; i += blockDim.x) {    // dQ (carries the forward scale)
     const int q = i >> 6, c = i & 63;
     float s = 0.f;
     for (int j = 0; j < Lk; ++j) s += dS[q * Lk + j] * K[j * 65 + c];
     obase[q * ldq + h * 64 + c] = __float2bfloat16(s * scale);
   }
-  for (int i = threadIdx.x; i < Lk * 64; i += 256) {   // dK, dV
+  for (int i = threadIdx.x; i < Lk * 64; i += blockDim.x) {   // dK, dV
     const int j = i >> 6, c = i & 63, t = j / mult, r = j % mult;
     float sk = 0.f, sv = 0.f;
     for (int q = 0; q < L; ++q) {
@@ -644,7 +645,7 @@ extern "C" int af_attention_small_bwd(const void* qkv, long long ldq, int k_off,
   const size_t smem = (static_cast<size_t>(2) * L * 64 + static_cast<size_t>(2) * Lk * 65 + static_cast<size_t>(2) * L * Lk) * 4;
   AF_CHECK_ARG(smem <= 227 * 1024, "af_attention_small_bwd: L=%d mult=%d needs %zu bytes of shared memory", L, mult, smem);
   AF_CUDA(cudaFuncSetAttribute(attention_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  attention_small_bwd_kernel<<<B * heads, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ldq, k_off, v_off,
+  attention_small_bwd_kernel<<<B * heads, 1024, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ldq, k_off, v_off,
                                                                static_cast<const __nv_bfloat16*>(dout), ldo,
                                                                static_cast<__nv_bfloat16*>(dqkv), heads, L, mult, scale, causal);
   AF_LAUNCH_CHECK("attention_small_bwd_kernel");
