@@ -376,6 +376,13 @@ int attention_pair_dispatch(const void* Q, long long ldq, const void* K, long lo
 int xattn_dispatch(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
                    int kv_stride, const unsigned char* key_mask, void* O, int B, int heads, int Nq, int Nk, int d,
                    float* lse, cudaStream_t stream);  // xattn.cu
+int attention_tile_dispatch(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
+                            int kv_stride, const unsigned char* key_mask, void* O, int B, int heads, int Nq, int Nk,
+                            int d, float* lse, int variant, cudaStream_t stream);  // attention_tile.cu
+int attention_stream_dispatch(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
+                              int kv_stride, const unsigned char* key_mask, void* O, int B, int heads, int Nq, int Nk,
+                              float* lse, int poly, cudaStream_t stream);  // attention_tile.cu
+int attention_variant();  // attention_pair.cu
 }
 
 using namespace af;
@@ -402,6 +409,13 @@ extern "C" int af_attention_bf16_lse(const void* Q, long long ldq, const void* K
   AF_CHECK_ARG(B == 1 || kv_stride % 8 == 0, "af_attention_bf16: kv_stride=%d must be a multiple of 8 when B > 1", kv_stride);
   if (Nq >= 256 && Nk <= 128 && (d == 40 || d == 80))    // short context, K / V resident per (sample, head) (xattn.cu)
     return xattn_dispatch(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, B, heads, Nq, Nk, d, lse, stream);
+  const int var = attention_variant();
+  if (Nq >= 256 && Nk > 128 && d == 40 && (var & 64))   // streamed 64-key blocks, three S buffers (attention_tile.cu)
+    return attention_stream_dispatch(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, B, heads, Nq, Nk, lse, var & 15,
+                                     stream);
+  if (Nq >= 256 && Nk > 128 && (var & 16) && (d == 40 || (d == 80 && (var & 32))))   // one tile per CTA, two CTAs per SM
+    return attention_tile_dispatch(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, B, heads, Nq, Nk, d, lse, var & 15,
+                                   stream);
   if (Nq >= 256 && (d == 40 || (d == 80 && Nk <= 128)))  // two query tiles per CTA (attention_pair.cu)
     return attention_pair_dispatch(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, B, heads, Nq, Nk, d, lse, stream);
   AttnParams p;

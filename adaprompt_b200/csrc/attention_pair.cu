@@ -816,6 +816,7 @@ __global__ void __launch_bounds__(640, 1) attention_rowsplit_kernel(const __grid
 }
 
 static long long* g_pair_trace = nullptr;
+int attention_variant();
 static int g_pair_variant = AF_ATTN_PAIR_VARIANT;   // bit 0: split hand-off, bit 1: P in tensor memory, bit 2: ping-pong
 
 template <int D, bool SPLIT, bool PTMEM>
@@ -897,6 +898,9 @@ int attention_pair_dispatch(const void* Q, long long ldq, const void* K, long lo
   return d == 40 ? launch_pair<40>(p, stream) : launch_pair<80>(p, stream);
 }
 
+int attention_variant() { return g_pair_variant; }
+long long* attention_trace_ptr() { return g_pair_trace; }
+
 }  // namespace af
 
 extern "C" int af_attention_set_trace(long long* device_buffer) {
@@ -906,6 +910,6 @@ extern "C" int af_attention_set_trace(long long* device_buffer) {
 
 extern "C" int af_attention_set_pair_variant(int variant) {
   const int old = af::g_pair_variant;
-  if (variant >= 0) af::g_pair_variant = variant & 15;
+  if (variant >= 0) af::g_pair_variant = variant & 0xffff;
   return old;
 }
