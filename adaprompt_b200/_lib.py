@@ -61,8 +61,8 @@ SIGNATURES = {
     "af_conv3x3_gn_slots": (c_int, [c_int, c_int]),
     "af_gemm_set_pair_mode": (c_int, [c_int]),
     "af_gemm_set_trace": (c_int, [c_void_p]),
-    "af_attention_set_pair_variant": (c_int, [c_int]),
-    "af_attention_set_trace": (c_int, [c_void_p]),
+    "af_attention_bf16_trace": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_void_p,
+                                        c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "af_groupnorm_workspace_bytes": (c_size_t, [c_int, c_int]),
     "af_groupnorm_stats_slots": (c_int, [c_int, c_int]),
     "af_groupnorm_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),

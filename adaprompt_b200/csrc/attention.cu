@@ -370,36 +370,44 @@ static int launch_attention(const AttnParams& p, cudaStream_t stream) {
 }  // namespace af
 
 namespace af {
-int attention_pair_dispatch(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
-                            int kv_stride, const unsigned char* key_mask, void* O, int B, int heads, int Nq, int Nk,
-                            int d, float* lse, cudaStream_t stream);  // attention_pair.cu
 int xattn_dispatch(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
                    int kv_stride, const unsigned char* key_mask, void* O, int B, int heads, int Nq, int Nk, int d,
                    float* lse, cudaStream_t stream);  // xattn.cu
 int attention_tile_dispatch(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
                             int kv_stride, const unsigned char* key_mask, void* O, int B, int heads, int Nq, int Nk,
-                            int d, float* lse, int variant, cudaStream_t stream);  // attention_tile.cu
-int attention_stream_dispatch(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
-                              int kv_stride, const unsigned char* key_mask, void* O, int B, int heads, int Nq, int Nk,
-                              float* lse, int poly, cudaStream_t stream);  // attention_tile.cu
-int attention_variant();  // attention_pair.cu
+                            int d, float* lse, long long* trace, cudaStream_t stream);  // attention_tile.cu
 }
 
 using namespace af;
 
-extern "C" int af_attention_bf16_lse(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt,
-                                     long long ldvt, int kv_stride, const unsigned char* key_mask, void* O, float* lse,
-                                     int B, int heads, int Nq, int Nk, int d, cudaStream_t stream);
+static int attention_impl(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
+                          int kv_stride, const unsigned char* key_mask, void* O, float* lse, long long* trace, int B,
+                          int heads, int Nq, int Nk, int d, cudaStream_t stream);
 
 extern "C" int af_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt,
                                  long long ldvt, int kv_stride, const unsigned char* key_mask, void* O, int B,
                                  int heads, int Nq, int Nk, int d, cudaStream_t stream) {
-  return af_attention_bf16_lse(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, nullptr, B, heads, Nq, Nk, d, stream);
+  return attention_impl(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, nullptr, nullptr, B, heads, Nq, Nk, d, stream);
 }
 
 extern "C" int af_attention_bf16_lse(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt,
                                      long long ldvt, int kv_stride, const unsigned char* key_mask, void* O, float* lse,
                                      int B, int heads, int Nq, int Nk, int d, cudaStream_t stream) {
+  return attention_impl(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, lse, nullptr, B, heads, Nq, Nk, d, stream);
+}
+
+extern "C" int af_attention_bf16_trace(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt,
+                                       long long ldvt, int kv_stride, void* O, long long* trace, int B, int heads, int Nq,
+                                       int Nk, int d, cudaStream_t stream) {
+  AF_CHECK_ARG(trace != nullptr, "af_attention_bf16_trace: null trace buffer");
+  AF_CHECK_ARG((d == 40 || d == 80) && Nk > 128 && Nk % (d == 40 ? 128 : 64) == 0,
+               "af_attention_bf16_trace: only the long-sequence d = 40 / 80 kernel with whole key blocks has a timeline");
+  return attention_impl(Q, ldq, K, ldk, Vt, ldvt, kv_stride, nullptr, O, nullptr, trace, B, heads, Nq, Nk, d, stream);
+}
+
+static int attention_impl(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
+                          int kv_stride, const unsigned char* key_mask, void* O, float* lse, long long* trace, int B,
+                          int heads, int Nq, int Nk, int d, cudaStream_t stream) {
   AF_CHECK_ARG(Q && K && Vt && O, "af_attention_bf16: null pointer");
   AF_CHECK_ARG(d == 40 || d == 80 || d == 160, "af_attention_bf16: head dim %d unsupported (40/80/160)", d);
   AF_CHECK_ARG(B > 0 && heads > 0 && Nq > 0 && Nk > 0 && kv_stride >= Nk, "af_attention_bf16: bad sizes");
@@ -409,15 +417,9 @@ extern "C" int af_attention_bf16_lse(const void* Q, long long ldq, const void* K
   AF_CHECK_ARG(B == 1 || kv_stride % 8 == 0, "af_attention_bf16: kv_stride=%d must be a multiple of 8 when B > 1", kv_stride);
   if (Nq >= 256 && Nk <= 128 && (d == 40 || d == 80))    // short context, K / V resident per (sample, head) (xattn.cu)
     return xattn_dispatch(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, B, heads, Nq, Nk, d, lse, stream);
-  const int var = attention_variant();
-  if (Nq >= 256 && Nk > 128 && d == 40 && (var & 64))   // streamed 64-key blocks, three S buffers (attention_tile.cu)
-    return attention_stream_dispatch(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, B, heads, Nq, Nk, lse, var & 15,
-                                     stream);
-  if (Nq >= 256 && Nk > 128 && (var & 16) && (d == 40 || (d == 80 && (var & 32))))   // one tile per CTA, two CTAs per SM
-    return attention_tile_dispatch(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, B, heads, Nq, Nk, d, lse, var & 15,
+  if (Nk > 128 && (d == 40 || d == 80))                  // one query tile per CTA, two CTAs per SM (attention_tile.cu)
+    return attention_tile_dispatch(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, B, heads, Nq, Nk, d, lse, trace,
                                    stream);
-  if (Nq >= 256 && (d == 40 || (d == 80 && Nk <= 128)))  // two query tiles per CTA (attention_pair.cu)
-    return attention_pair_dispatch(Q, ldq, K, ldk, Vt, ldvt, kv_stride, key_mask, O, B, heads, Nq, Nk, d, lse, stream);
   AttnParams p;
   memset(&p, 0, sizeof(p));
   const int dp = d == 40 ? 48 : d;

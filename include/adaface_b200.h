@@ -80,17 +80,6 @@ int af_gemm_set_pair_mode(int mode);
  * tile done).  Null switches it off. */
 int af_gemm_set_trace(long long* device_buffer);
 
-/* Schedule of the two-query-tile self-attention kernel (head dims 40 / 80, Nq >= 256), for A/B measurements:
- * bit 0 = hand P to the PV MMA per 64-key piece instead of per key block, bit 1 = pass P through tensor memory
- * (A-operand-in-TMEM MMA) instead of shared memory, bit 2 = the two softmax warps of an SM sub-partition take turns
- * in the ex2 phase (ping-pong).  variant < 0 only queries.  Returns the previous variant. */
-int af_attention_set_pair_variant(int variant);
-/* Timeline probe of the same kernel: when device_buffer (>= 4*64*8 int64, caller-owned) is non-null, CTA (0,0,0) of every
- * following launch records clock64 stamps: [actor: softmax warp of tile 0, of tile 1, MMA issuer 0, 1][key block < 64][8 events]
- * (softmax: loop top, S ready, S in registers, max done, {P piece free, P piece handed over} x pieces; MMA: S issue
- * begin / end, {PV piece begin / end}).  Null switches it off.  Measurement aid only - results are unaffected. */
-int af_attention_set_trace(long long* device_buffer);
-
 /* 3x3 convolution, pad 1, stride 1 or 2, NHWC bf16 input(s) [B,H,W,C0] (+ [B,H,W,C1] concat), weights
  * Wt[Cout][ky][kx][C0+C1] bf16, as an implicit GEMM (no im2col buffer).  Output rows are output pixels
  * (n, oh, ow) row-major.  Replaces nn.Conv2d 3x3 at openaimodel.py:155 (stride 2), :208, :234, :120-122. */
@@ -113,6 +102,15 @@ int af_attention_bf16(const void* Q, long long ldq, const void* K, long long ldk
 int af_attention_bf16_lse(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
                           int kv_stride, const unsigned char* key_mask, void* O, float* lse, int B, int heads, int Nq,
                           int Nk, int d, af_stream_t stream);
+
+/* af_attention_bf16 on the long-sequence kernel (d in {40, 80}, Nk > 128 and a multiple of 128 / 64, no mask) with an
+ * in-kernel clock64 timeline - a measurement aid (scripts/attn_tile_trace.py), results are those of af_attention_bf16.
+ * trace: caller-owned device buffer of 512*64*8 + 512 + 2*64*8 int64: [first 512 CTAs (linear id)][key block < 64][8]
+ * stamps of softmax warp 4 (loop top, S ready, S in registers, reference decided, P buffer free, exponentials issued, P
+ * handed over); then the SM id of each of those CTAs; then [MMA issuer, TMA producer of CTA 0][64][8]. */
+int af_attention_bf16_trace(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
+                            int kv_stride, void* O, long long* trace, int B, int heads, int Nq, int Nk, int d,
+                            af_stream_t stream);
 
 /* GroupNorm(32) over the channel concat [x0 | x1] of fp32 NHWC tensors, optional SiLU, bf16 output
  * [B, HW, C0+C1]; optional raw bf16 copy of the concat (operand of the 1x1 skip conv).

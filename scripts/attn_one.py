@@ -1,8 +1,7 @@
 """One self-attention launch at the headline shape (B16, N4096, d40) for ncu."""
 import sys, torch
 sys.path.insert(0, ".")
-from adaprompt_b200 import ops, _lib
-if len(sys.argv) > 1: _lib.load().af_attention_set_pair_variant(int(sys.argv[1]))
+from adaprompt_b200 import ops
 B, heads, N, d, dp = 16, 8, 4096, 40, 48
 q = torch.randn(B * N, 2 * heads * dp, device="cuda").to(torch.bfloat16) * 0.3
 vt = torch.randn(heads * d, B * N, device="cuda").to(torch.bfloat16)

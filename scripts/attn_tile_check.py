@@ -1,16 +1,12 @@
-"""A/B of the self-attention schedules: parity of each variant on a few shapes (incl. ragged / masked), then timing at
-the UNet's batch-16 shapes.  Usage: attn_tile_check.py v1,v2,... [reps]
-variant < 16: round-1 pair / row-split kernels; 16 + x: attention_tile.cu (bit 0 two threads per row, bits 1-2 FMA-pipe
-share of the exponentials); + 32: d = 80 through the tile kernel as well."""
+"""Self-attention kernels: parity on a few shapes (incl. ragged / masked), then timing at the UNet's batch-16 shapes.
+Usage: attn_tile_check.py [reps]"""
 import sys, math, torch
 sys.path.insert(0, ".")
 sys.path.insert(0, "tests")
-from adaprompt_b200 import ops, _lib
+from adaprompt_b200 import ops
 import test_kernels_gpu as T
 
-variants = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [8, 16, 17]
-reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-lib = _lib.load()
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 B, heads = 16, 8
 
 def bench(N, d):
@@ -29,24 +25,13 @@ def bench(N, d):
     for _ in range(reps): f()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    fl = 4.0 * B * heads * N * N * d
-    return ms, fl / ms / 1e9
+    return ms, 4.0 * B * heads * N * N * d / ms / 1e9
 
-for var in variants:
-    lib.af_attention_set_pair_variant(var)
-    errs = []
-    try:
-        errs.append(("40/4096", T._attn_case(1, 4096, 4096, 40)))
-        errs.append(("40/1000m", T._attn_case(2, 1000, 1000, 40, seed=3, mask=True)))
-        errs.append(("40/296", T._attn_case(3, 296, 296, 40, seed=4)))
-        errs.append(("80/1024", T._attn_case(2, 1024, 1024, 80)))
-        errs.append(("80/1000m", T._attn_case(2, 1000, 1000, 80, seed=7, mask=True)))
-    except Exception as e:  # noqa
-        print(f"variant {var}: FAILED {e!r}", flush=True)
-        continue
-    torch.cuda.synchronize()
-    ok = all(e < 6e-3 for _, e in errs)
-    t40 = bench(4096, 40)
-    t80 = bench(1024, 80)
-    print(f"variant {var:3d}: parity {'ok ' if ok else 'BAD'} " + " ".join(f"{n}={e:.2e}" for n, e in errs) +
-          f" | N4096 d40 {t40[0]:.3f} ms {t40[1]:.0f} TF/s | N1024 d80 {t80[0]:.3f} ms {t80[1]:.0f} TF/s", flush=True)
+errs = [("40/4096", T._attn_case(1, 4096, 4096, 40)), ("40/1000m", T._attn_case(2, 1000, 1000, 40, seed=3, mask=True)),
+        ("40/296", T._attn_case(3, 296, 296, 40, seed=4)), ("80/1024", T._attn_case(2, 1024, 1024, 80)),
+        ("80/1000m", T._attn_case(2, 1000, 1000, 80, seed=7, mask=True))]
+torch.cuda.synchronize()
+print("parity " + ("ok " if all(e < 6e-3 for _, e in errs) else "BAD ") + " ".join(f"{n}={e:.2e}" for n, e in errs))
+for N, d in ((4096, 40), (9216, 40), (1024, 80), (2304, 80), (256, 160), (64, 160)):
+    ms, tf = bench(N, d)
+    print(f"N={N:5d} d={d:3d}: {ms:8.3f} ms  {tf:7.1f} TFLOP/s", flush=True)

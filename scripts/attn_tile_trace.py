@@ -1,11 +1,9 @@
-"""Device timeline of the tile attention kernel (N=4096, d=40 or N=1024, d=80). Usage: attn_tile_trace.py [d] [variant]"""
+"""Device timeline of the tile attention kernel (N=4096, d=40 or N=1024, d=80). Usage: attn_tile_trace.py [d]"""
 import sys, torch, statistics as st
 sys.path.insert(0, ".")
 from adaprompt_b200 import ops, _lib
 d = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-var = int(sys.argv[2]) if len(sys.argv) > 2 else 16 | 32
 lib = _lib.load()
-lib.af_attention_set_pair_variant(var)
 B, heads = 16, 8
 N = 4096 if d == 40 else 1024
 dp = 48 if d == 40 else d
@@ -17,9 +15,10 @@ f = lambda: ops.attention(q, k, vt, o, B=B, heads=heads, Nq=N, d=d, ldq=2 * head
 f(); torch.cuda.synchronize()
 NC = 512
 buf = torch.zeros(NC * 64 * 8 + NC + 2 * 64 * 8, dtype=torch.int64, device="cuda")
-lib.af_attention_set_trace(buf.data_ptr())
-f(); torch.cuda.synchronize()
-lib.af_attention_set_trace(None)
+rc = lib.af_attention_bf16_trace(q.data_ptr(), 2 * heads * dp, k.data_ptr(), 2 * heads * dp, vt.data_ptr(), B * N, N,
+                                 o.data_ptr(), buf.data_ptr(), B, heads, N, N, d, torch.cuda.current_stream().cuda_stream)
+_lib.check(rc, "af_attention_bf16_trace")
+torch.cuda.synchronize()
 h = buf.cpu()
 t = h[:NC * 64 * 8].view(NC, 64, 8)
 smid = h[NC * 64 * 8:NC * 64 * 8 + NC].tolist()
@@ -31,21 +30,13 @@ def phases(rows_t, names, nev):
     durs = [[r[i + 1] - r[i] for r in rows] for i in range(nev - 1)] + [[n - r[nev - 1] for r, n in zip(rows, nxt)]]
     per = st.mean([n - r[0] for r, n in zip(rows, nxt)])
     return ", ".join(f"{nm} {st.mean(dd):.0f}" for nm, dd in zip(names, durs)) + f" | period {per:.0f}"
-stream = bool(var & 64)
-if stream:
-    lo, hi = 8, 56
-    nb = N // 64
 sm = ["wait S", "ld S", "max", "wait P free", "exp+st issue", "st drain+arrive", "loop"]
 NEV, NEV_I, EXP0, EXP1 = 7, 7, 4, 5
 inames = ["wait K", "wait S free", "issue S", "wait V", "wait P", "issue PV", "loop"]
-if stream:
-    sm = ["wait S(j+1)+ld issue", "exp (+max guard)", "st+drain+arrive", "ld wait", "loop"]
-    inames = ["wait V", "wait P", "issue PV", "wait K + issue S(j+3)", "loop"]
-    NEV, NEV_I, EXP0, EXP1 = 5, 5, 1, 2
-print(f"d={d} N={N} variant {var}: cycles per key block, blocks {lo}..{hi}")
+print(f"d={d} N={N}: cycles per key block, blocks {lo}..{hi}")
 print("softmax CTA0:", phases(t[0], sm, NEV))
 print("issuer      :", phases(t2[0], inames, NEV_I))
-if not stream: print("producer    :", phases(t2[1], ["wait K slot", "issue K", "wait V slot", "issue V+loop"], 4))
+print("producer    :", phases(t2[1], ["wait K slot", "issue K", "wait V slot", "issue V+loop"], 4))
 # co-resident partner of CTA 0 in the first wave: same SM, start within 20k cycles
 part = [c for c in range(1, NC) if smid[c] == smid[0] and abs(int(t[c, 0, 0]) - int(t[0, 0, 0])) < 20000]
 print("CTA 0 on SM", smid[0], "first-wave partners:", part)

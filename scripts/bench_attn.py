@@ -29,13 +29,7 @@ def run(N, Nk, d, cross):
     ms = e0.elapsed_time(e1) / reps
     fl = 4.0 * B * heads * N * kw["Nk"] * d
     print(f"N={N:5d} Nk={kw['Nk']:5d} d={d:3d} {'cross' if cross else 'self '}: {ms:8.3f} ms  {fl/ms/1e9:8.1f} TFLOP/s", flush=True)
-from adaprompt_b200 import _lib
-variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [_lib.load().af_attention_set_pair_variant(-1)]
-for var in variants:
-    _lib.load().af_attention_set_pair_variant(var)
-    print(f"--- pair variant {var} (bit0 split hand-off, bit1 P in TMEM)")
-    for (N, d) in ((4096, 40), (1024, 80), (256, 160), (64, 160)):
-        if only and d != only: continue
-        if len(variants) > 1 and d > 80: continue
-        run(N, N, d, False)
-        if len(variants) == 1: run(N, 77, d, True)
+for (N, d) in ((4096, 40), (1024, 80), (256, 160), (64, 160)):
+    if only and d != only: continue
+    run(N, N, d, False)
+    run(N, 77, d, True)
