@@ -11,9 +11,42 @@ from torch import nn
 from . import ops
 
 
+class _ScaleGradFn(torch.autograd.Function):
+    """adaface/util.py:28-47 ScaleGrad: identity forward, gradient times alpha."""
+
+    @staticmethod
+    def forward(ctx, x, alpha):
+        ctx.alpha = float(alpha)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.alpha, None
+
+
+class GradientScaler(nn.Module):
+    """What gen_gradient_scaler returns for alpha not in {0, 1}: identity forward, d/dx scaled by alpha."""
+
+    def __init__(self, alpha):
+        super().__init__()
+        self.alpha = float(alpha)
+
+    def forward(self, x):
+        return _ScaleGradFn.apply(x, self.alpha) if torch.is_grad_enabled() and x.requires_grad else x
+
+
+class _Detach(nn.Module):
+    def forward(self, x):
+        return x.detach()
+
+
 def gen_gradient_scaler(alpha, debug=False):
-    """adaface/util.py:60-72.  Forward is the identity; the backward scaling only matters for training (row T1)."""
-    return nn.Identity()
+    """adaface/util.py:60-72: alpha 1 -> identity, alpha 0 -> detach, otherwise a gradient scaler (forward identity)."""
+    if alpha == 1:
+        return nn.Identity()
+    if alpha > 0:
+        return GradientScaler(alpha)
+    return _Detach()
 
 
 def _tokenize(tokenizer, text, max_length, device):

@@ -45,26 +45,41 @@ def Normalize(in_channels):
 
 
 class PackedModule(nn.Module):
-    """Lazily repacks fp32 reference-layout parameters into kernel layouts; invalidated whenever the
-    parameters move (.to/.cuda) or are reloaded (load_state_dict)."""
+    """Lazily repacks fp32 reference-layout parameters into kernel layouts.  The packs (forward `_pk`, the transposed
+    dgrad packs `_pk_bwd` of train.py and the frozen-layer training packs `_train_pk` of train_cond.py) are keyed on the
+    (storage pointer, version counter) of every source parameter: an optimizer step, an in-place copy, a re-bound
+    `.data`, `.to()` or `load_state_dict` all change the key and the next use repacks."""
+
+    PACK_EPOCH = 0   # bumped on every repack of any module: graph_sampler re-captures when it changes
 
     def _pack(self) -> dict:
         raise NotImplementedError
 
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
     def packed(self) -> dict:
         pk = self.__dict__.get("_pk")
-        if pk is None:
+        key = self._param_key()
+        if pk is None or self.__dict__.get("_pk_key") != key:
             dev = next(self.parameters()).device
             if dev.type != "cuda":
                 raise RuntimeError(f"{type(self).__name__}: parameters are on {dev}; the B200 path has no CPU "
                                    "fallback - move the module to a CUDA device first")
+            if pk is not None:
+                self.invalidate_packed()
             with torch.no_grad():
                 pk = self._pack()
             self.__dict__["_pk"] = pk
+            self.__dict__["_pk_key"] = key
+            PackedModule.PACK_EPOCH += 1
         return pk
 
     def invalidate_packed(self):
         self.__dict__["_pk"] = None
+        self.__dict__["_pk_key"] = None
+        self.__dict__.pop("_pk_bwd", None)
+        self.__dict__.pop("_train_pk", None)
 
     def _apply(self, fn, *a, **k):
         r = super()._apply(fn, *a, **k)

@@ -285,13 +285,14 @@ __global__ void __launch_bounds__(256) upsample2x_cast_kernel(const float* __res
 // coef row: [g, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef, sigma*temperature, 0, 0]
 // eps holds the conditional half first, then the unconditional half (ddim.py:238-243); n = elements per half.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) cfg_ddim_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+// x and x_prev may alias (the graph path updates the latent in place): no __restrict__ on them
+__global__ void __launch_bounds__(256) cfg_ddim_kernel(const float* x, const float* __restrict__ eps,
                                                        int has_uncond, const float* __restrict__ noise,
                                                        const float* __restrict__ coef_table,
-                                                       const int* __restrict__ step_idx, float* __restrict__ x_prev,
+                                                       const int* __restrict__ step_idx, float* x_prev,
                                                        float* __restrict__ pred_x0, size_t n) {
   const float* cf = coef_table + (step_idx ? static_cast<size_t>(*step_idx) * 8 : 0);
-  const float g = cf[0], s1m = cf[1], sat = cf[2], sap = cf[3], dcoef = cf[4], sig = cf[5];
+  const float g = cf[0], s1m = cf[1], sat = cf[2], sap = cf[3], dcoef = cf[4], sig = cf[5], temp = cf[6];
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float e = eps[i];
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(256) cfg_ddim_kernel(const float* __restrict__
     const float pred = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(s1m, e)), sat);
     const float dir = __fmul_rn(dcoef, e);
     float xp = __fadd_rn(__fmul_rn(sap, pred), dir);
-    const float nz = noise ? __fmul_rn(sig, noise[i]) : 0.f;
+    const float nz = noise ? __fmul_rn(__fmul_rn(sig, noise[i]), temp) : 0.f;   // (sigma * noise) * temperature, ddim.py:286
     xp = __fadd_rn(xp, nz);
     x_prev[i] = xp;
     if (pred_x0) pred_x0[i] = pred;

@@ -1,5 +1,13 @@
-"""Host-side schedule helpers mirroring ldm/modules/diffusionmodules/util.py (scalar / 1000-element
-vector work that the reference also does on the host in numpy)."""
+"""Host-side schedule arithmetic of the sampler (scalar / 1000-element vector work; numpy float64 like the reference's
+host code, cast to fp32 where the reference casts).
+
+What the SD-1.5 / AdaFace configuration actually uses (configs/stable-diffusion/v1-inference-ada.yaml:5-9 and
+DDIMSampler.make_schedule, ldm/models/diffusion/ddim.py:28-68):
+  * beta schedule "linear" (linear in sqrt(beta), ldm/modules/diffusionmodules/util.py:23-25),
+  * "uniform" DDIM time-step selection (util.py:48-50,57),
+  * sigma_t = eta * sqrt((1 - a_prev) / (1 - a_t) * (1 - a_t / a_prev)) (util.py:63-69).
+Other schedule names the reference's helper accepts are not part of this path and raise.
+"""
 from __future__ import annotations
 
 import numpy as np
@@ -7,57 +15,39 @@ import torch
 
 
 def make_beta_schedule(schedule, n_timestep, linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3):
-    """util.py:21-43."""
-    if schedule == "linear":
-        betas = torch.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=torch.float64) ** 2
-    elif schedule == "cosine":
-        timesteps = torch.arange(n_timestep + 1, dtype=torch.float64) / n_timestep + cosine_s
-        alphas = timesteps / (1 + cosine_s) * np.pi / 2
-        alphas = torch.cos(alphas).pow(2)
-        alphas = alphas / alphas[0]
-        betas = 1 - alphas[1:] / alphas[:-1]
-        betas = np.clip(betas, a_min=0, a_max=0.999)
-    elif schedule == "sqrt_linear":
-        betas = torch.linspace(linear_start, linear_end, n_timestep, dtype=torch.float64)
-    elif schedule == "sqrt":
-        betas = torch.linspace(linear_start, linear_end, n_timestep, dtype=torch.float64) ** 0.5
-    else:
-        raise ValueError(f"schedule '{schedule}' unknown.")
-    return betas.numpy()
+    """float64 numpy betas.  Only schedule == "linear": equally spaced in sqrt(beta), then squared."""
+    if schedule != "linear":
+        raise NotImplementedError(f"beta schedule '{schedule}': the AdaFace / SD-1.5 path uses 'linear' only")
+    root = torch.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=torch.float64)
+    return (root * root).numpy()
 
 
 def make_ddim_timesteps(ddim_discr_method, num_ddim_timesteps, num_ddpm_timesteps, verbose=True):
-    """util.py:46-60."""
-    if ddim_discr_method == "uniform":
-        c = num_ddpm_timesteps // num_ddim_timesteps
-        ddim_timesteps = np.asarray(list(range(0, num_ddpm_timesteps, c)))
-    elif ddim_discr_method == "quad":
-        ddim_timesteps = ((np.linspace(0, np.sqrt(num_ddpm_timesteps * .8), num_ddim_timesteps)) ** 2).astype(int)
-    else:
-        raise NotImplementedError(f'There is no ddim discretization method called "{ddim_discr_method}"')
-    steps_out = ddim_timesteps + 1
-    if verbose:
-        print(f"Selected timesteps for ddim sampler: {steps_out}")
-    return steps_out
+    """Every (T // S)-th training step, shifted by one: 1, 21, ..., 981 for S = 50, T = 1000."""
+    if ddim_discr_method != "uniform":
+        raise NotImplementedError(f"ddim discretisation '{ddim_discr_method}': only 'uniform' is on this path")
+    stride = num_ddpm_timesteps // num_ddim_timesteps
+    return np.arange(0, num_ddpm_timesteps, stride) + 1
 
 
 def make_ddim_sampling_parameters(alphacums, ddim_timesteps, eta, verbose=True):
-    """util.py:63-77 (alphacums is a CPU fp32 tensor, exactly as DDIMSampler.make_schedule passes it)."""
+    """(sigmas, alphas, alphas_prev) of the selected steps.  alphacums: CPU fp32 tensor (as make_schedule passes it);
+    alphas stays an fp32 tensor, alphas_prev / sigmas become float64 numpy arrays of fp32 values - the mixed types are
+    what the reference's arithmetic sees, and the fp32 coefficient rows are derived from exactly these."""
     alphas = alphacums[ddim_timesteps]
-    alphas_prev = np.asarray([alphacums[0]] + alphacums[ddim_timesteps[:-1]].tolist())
+    shifted = alphacums[ddim_timesteps[:-1]].tolist()
+    alphas_prev = np.asarray([alphacums[0]] + shifted)
     sigmas = eta * np.sqrt((1 - alphas_prev) / (1 - alphas) * (1 - alphas / alphas_prev))
-    if verbose:
-        print(f"Selected alphas for ddim sampler: a_t: {alphas}; a_(t-1): {alphas_prev}")
-        print(f"For the chosen value of eta, which is {eta}, "
-              f"this results in the following sigma_t schedule for ddim sampler {sigmas}")
     return sigmas, alphas, alphas_prev
 
 
 def noise_like(shape, device, repeat=False):
-    """util.py:267-270."""
-    if repeat:
-        return torch.randn((1, *shape[1:]), device=device).repeat(shape[0], *((1,) * (len(shape) - 1)))
-    return torch.randn(shape, device=device)
+    """One standard-normal draw per call from the global generator of `device` (util.py:267-270); with `repeat` the
+    first sample's noise is shared by the batch."""
+    if not repeat:
+        return torch.randn(shape, device=device)
+    one = torch.randn((1, *shape[1:]), device=device)
+    return one.expand(shape[0], *shape[1:]).contiguous()
 
 
 def timestep_embedding(timesteps, dim, max_period=10000, repeat_only=False):

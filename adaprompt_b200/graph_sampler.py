@@ -19,21 +19,33 @@ from typing import Optional
 import torch
 
 from . import _lib, ops
+from .attention import PackedModule
 from .diffusion_util import noise_like
 
 
+_UNET_FLAGS = ("use_layerwise_context", "iter_type", "is_training", "capture_distill_attn", "use_conv_attn_kernel_size",
+               "apply_compel_cfg_prob", "debug_attn")
+
+
 def _extra_key(extra_info: Optional[dict]):
-    """Hashable summary of the run-time flags baked into a captured graph; None -> not cacheable."""
+    """Hashable summary of what a captured graph bakes in: exactly the fields UNetModel.forward reads
+    (openaimodel.py:849-859).  placeholder2indices / prompt_emb_mask (always present in the output of
+    get_learned_conditioning) are only read by the conv-attention path, so they do not key the graph.
+    None -> not cacheable (a per-call tensor would be baked into the graph by address)."""
     if extra_info is None:
         return ()
+    if extra_info.get("img_mask", None) is not None:
+        return None
+    conv = extra_info.get("use_conv_attn_kernel_size", None)
+    if conv is not None and conv > 0 and extra_info.get("placeholder2indices", None) is not None:
+        return None
     items = []
-    for k, v in extra_info.items():
-        if k == "ca_layers_activations":
-            continue
+    for k in _UNET_FLAGS:
+        v = extra_info.get(k, None)
         if torch.is_tensor(v) or isinstance(v, (dict, list)):
             return None
         items.append((k, v))
-    return tuple(sorted(items, key=lambda kv: kv[0]))
+    return tuple(items)
 
 
 class _StepGraph:
@@ -61,6 +73,7 @@ class _StepGraph:
         self.graph = None
         self.kvs = None
         self.kernels = 0
+        self.pack_epoch = -1
         self._sampler = sampler
 
     def load_conditioning(self, cond, uncond):
@@ -87,6 +100,8 @@ class _StepGraph:
     def capture(self):
         """Warm-up on a side stream (packs weights, fills caches, warms the allocator), then capture."""
         saved = (self.x.clone(), self.step_idx.clone(), self.t_buf.clone())
+        self.step_idx.zero_()   # body() indexes the coefficient tables by the counter: a re-capture after a full run
+        #                          would otherwise read row `total` (== max_steps: out of bounds)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -95,9 +110,11 @@ class _StepGraph:
         self.x.copy_(saved[0]); self.step_idx.copy_(saved[1]); self.t_buf.copy_(saved[2])
         g = torch.cuda.CUDAGraph()
         n0 = _lib.TRACE.count
+        self.step_idx.zero_()
         with torch.cuda.graph(g):
             self.body(None)
         self.kernels = _lib.TRACE.count - n0
+        self.pack_epoch = PackedModule.PACK_EPOCH
         self.x.copy_(saved[0]); self.step_idx.copy_(saved[1]); self.t_buf.copy_(saved[2])
         self.graph = g
 
@@ -138,6 +155,8 @@ def run(sampler, img, cond, uncond, steps, scales, temperature, log_every_t, int
         st.coef_table[:total].copy_(coef_host, non_blocking=True)
         st.t_table[:total].copy_(t_host, non_blocking=True)
         st.load_conditioning(cond, uncond)
+        if st.graph is not None and st.pack_epoch != PackedModule.PACK_EPOCH:
+            st.graph = None     # some module repacked its weights since the capture: the graph holds stale pointers
         if st.graph is None:
             st.capture()
         if cond[2] is not None:

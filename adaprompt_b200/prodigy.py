@@ -16,6 +16,19 @@ import torch
 from . import _lib
 
 
+BUCKET_ALIGN = 64   # elements: every parameter starts on a 256-byte boundary of the flat buckets (kernels read the
+#                     parameter views with 16-byte vector loads / TMA)
+
+
+def flat_layout(params):
+    """-> (offsets, total) of the flat fp32 bucket layout shared by the parameter, state and gradient buckets."""
+    offs, o = [], 0
+    for p in params:
+        offs.append(o)
+        o += (p.numel() + BUCKET_ALIGN - 1) // BUCKET_ALIGN * BUCKET_ALIGN
+    return offs, o
+
+
 class Prodigy:
     def __init__(self, params: Iterable[torch.nn.Parameter], lr=1.0, betas=(0.9, 0.999), beta3=None, eps=1e-8,
                  weight_decay=0, decouple=True, use_bias_correction=False, safeguard_warmup=False, d0=1e-6,
@@ -51,12 +64,12 @@ class Prodigy:
         for p in self.params:
             if not p.is_cuda or p.dtype != torch.float32:
                 raise RuntimeError("Prodigy: parameters must be fp32 CUDA tensors (no CPU fallback)")
-        self.flat_p = torch.cat([p.data.reshape(-1) for p in self.params])
-        o = 0
-        for p in self.params:                       # parameters become views of the bucket
+        offs, total = flat_layout(self.params)
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=self.params[0].device)
+        for p, o in zip(self.params, offs):         # parameters become views of the bucket (aligned starts, zero gaps)
             n = p.numel()
+            self.flat_p[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.flat_p[o:o + n].view_as(p)
-            o += n
         self.p0 = self.flat_p.clone()
         self.s = torch.zeros_like(self.flat_p)
         self.exp_avg = torch.zeros_like(self.flat_p)
@@ -66,14 +79,17 @@ class Prodigy:
 
     @torch.no_grad()
     def step(self, flat_grad: Optional[torch.Tensor] = None):
-        """flat_grad: the fp32 gradient bucket in parameter order (as returned by allreduce_gradients), or None to
-        gather it from p.grad."""
+        """flat_grad: the fp32 gradient bucket in the flat_layout() of the parameters (train_cond.GradBucket.flat), or
+        None to gather it from p.grad."""
         if self.params is None and not self._init_state():
             return None
         if any(p.grad is None for p in self.params):
             raise RuntimeError("Prodigy: the set of parameters with gradients changed after the first step")
         if flat_grad is None:
-            flat_grad = torch.cat([p.grad.reshape(-1).float() for p in self.params])
+            offs, total = flat_layout(self.params)
+            flat_grad = torch.zeros(total, dtype=torch.float32, device=self.flat_p.device)
+            for p, o in zip(self.params, offs):
+                flat_grad[o:o + p.numel()].copy_(p.grad.reshape(-1))
         n = self.flat_p.numel()
         if flat_grad.numel() != n or flat_grad.dtype != torch.float32 or not flat_grad.is_contiguous():
             raise ValueError("Prodigy.step: gradient bucket does not match the parameter bucket")

@@ -471,3 +471,52 @@ def distill_loss(eps: torch.Tensor, teacher_eps: torch.Tensor, num_denoising_ste
     """Whole-image MSE against the teacher's noise (calc_recon_loss ddpm.py:3571-3595 with no masks, :3010-3013),
     scaled by 1/sqrt(steps) (:3037)."""
     return torch.nn.functional.mse_loss(eps, teacher_eps) / math.sqrt(num_denoising_steps)
+
+
+class GraphedUNetLoss:
+    """loss = distill_loss(UNet(x_noisy, t, c), teacher_eps) and dloss/dc replayed from ONE CUDA graph.
+
+    The UNet is frozen (ddpm.py:783-786), so the ~3500 kernel launches of its forward and backward-to-context depend
+    only on the shapes: they are captured once per geometry (static input / output buffers, torch.autograd.grad inside
+    the capture) and replayed per micro-batch - the host-side launch gaps of the eager tape (a fifth of the step)
+    disappear.  Weights are read through the version-keyed packs, so a repack invalidates the capture."""
+
+    def __init__(self, unet: UNetModel, extra_info: dict):
+        self.unet, self.extra_info = unet, dict(extra_info)
+        self._g = {}
+
+    def _build(self, x, t, c, teacher):
+        from .attention import PackedModule
+        st = {"x": x.clone(), "t": t.clone(), "c": c.clone().requires_grad_(True), "teacher": teacher.clone()}
+
+        def run():
+            eps = unet_forward_train(self.unet, st["x"], st["t"], st["c"], dict(self.extra_info))
+            loss = distill_loss(eps, st["teacher"])
+            (gc,) = torch.autograd.grad(loss, st["c"])
+            return loss.detach(), gc
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                run()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            st["loss"], st["grad_c"] = run()
+        st["graph"], st["epoch"] = graph, PackedModule.PACK_EPOCH
+        return st
+
+    def __call__(self, x_noisy, t, c, teacher_eps):
+        from .attention import PackedModule
+        key = (tuple(x_noisy.shape), tuple(c.shape), t.dtype)
+        st = self._g.get(key)
+        if st is None or st["epoch"] != PackedModule.PACK_EPOCH:
+            st = self._g[key] = self._build(x_noisy, t, c, teacher_eps)
+        st["x"].copy_(x_noisy)
+        st["t"].copy_(t)
+        st["teacher"].copy_(teacher_eps)
+        with torch.no_grad():
+            st["c"].copy_(c)
+        st["graph"].replay()
+        return st["loss"].clone(), st["grad_c"].clone()

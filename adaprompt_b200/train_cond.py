@@ -22,24 +22,11 @@ import torch
 from torch.autograd import Function
 
 from . import ops
-from .adaface_util import _tokenize, arc2face_forward_face_embs
+from .adaface_util import _ScaleGradFn, _tokenize, arc2face_forward_face_embs
 from .clip_text import CLIPEncoderLayer, CLIPTextTransformer
 from .train import LayerNormFn, distill_loss, linear, unet_forward_train
 
 N_CA_LAYERS = 16
-
-
-class GradScale(Function):
-    """adaface/util.py:28-47 ScaleGrad: identity forward, gradient times alpha."""
-
-    @staticmethod
-    def forward(ctx, x, alpha):
-        ctx.alpha = float(alpha)
-        return x.view_as(x)
-
-    @staticmethod
-    def backward(ctx, g):
-        return g * ctx.alpha, None
 
 
 def grad_scale(x, alpha):
@@ -48,7 +35,7 @@ def grad_scale(x, alpha):
         return x
     if alpha == 0:
         return x.detach()
-    return GradScale.apply(x, alpha)
+    return _ScaleGradFn.apply(x, alpha)
 
 
 class QuickGeluFn(Function):
@@ -269,34 +256,88 @@ def trainable_parameters(sbg) -> List[torch.nn.Parameter]:
     return [p for p in sbg.parameters() if p.requires_grad]
 
 
+class GradBucket:
+    """The gradients of a FIXED trainable-parameter list as one flat fp32 buffer; every p.grad is a view of it.
+
+    * autograd accumulates micro-batch gradients straight into the bucket (no torch.cat, no copy-back);
+    * a parameter that got no gradient on this rank contributes zeros - the bucket has the same size on every rank,
+      which a collective needs (ranks with different sets of touched parameters would otherwise hang NCCL);
+    * the one data-path collective of the step is a single all-reduce of the bucket (NCCL over
+      NVLink / NVSwitch on GPUs, gloo in the CPU tests), SUM scaled to the mean (main.py:829 uses Lightning DDP);
+    * clipping by norm (ddpm.py:607, gradient_clip_val 0.5) is two kernels on the bucket and no host synchronisation;
+    * Prodigy.step consumes the bucket as it is."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter]):
+        self.params = list(params)
+        if not self.params:
+            raise ValueError("GradBucket: empty parameter list")
+        from .prodigy import flat_layout
+        dev = self.params[0].device
+        offs, total = flat_layout(self.params)      # same layout as Prodigy's parameter / state buckets (aligned starts)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.views = [self.flat[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, offs)]
+        self._work = None
+
+    def begin_step(self):
+        """Zero the bucket and (re-)bind p.grad to its views (an optimizer may have set them to None)."""
+        self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            if p.dtype != torch.float32:
+                raise TypeError("GradBucket: trainable parameters must be fp32")
+            p.grad = v
+
+    def allreduce(self, world_size: int, group=None, async_op: bool = False):
+        import torch.distributed as dist
+        if world_size <= 1:
+            return None
+        self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        self._scale = 1.0 / world_size
+        if not async_op:
+            self.wait()
+        return self._work
+
+    def wait(self):
+        if self._work is not None:
+            self._work.wait()
+        self._work = None
+        if getattr(self, "_scale", None) is not None:
+            self.flat.mul_(self._scale)
+            self._scale = None
+
+    def clip_(self, max_norm: float = 0.5) -> torch.Tensor:
+        """In-place clip by total norm; returns the norm before clipping as a 0-d tensor (no host sync)."""
+        total = torch.linalg.vector_norm(self.flat)
+        self.flat.mul_(torch.clamp(max_norm / (total + 1e-6), max=1.0))
+        return total
+
+
 def allreduce_gradients(params: Sequence[torch.nn.Parameter], world_size: int, group=None) -> Optional[torch.Tensor]:
-    """One flat fp32 bucket, one all-reduce (SUM), scaled to the mean: the only data-path collective of the step
-    (SURVEY.md section 8(e)).  NCCL over NVLink / NVSwitch on GPUs, gloo in the CPU tests.  Returns the bucket."""
-    import torch.distributed as dist
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
+    """Functional form over ad-hoc p.grad tensors: builds the fixed-size bucket (zeros where p.grad is None), all-reduces
+    it to the mean and writes the result back to every p.grad.  Returns the bucket."""
+    params = list(params)
+    if not params:
         return None
-    flat = torch.cat([g.reshape(-1).float() for g in grads])
-    if world_size > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat /= world_size
-    o = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[o:o + n].view_as(g))
-        o += n
-    return flat
+    grads = [p.grad for p in params]
+    bucket = GradBucket(params)
+    bucket.begin_step()
+    for v, g in zip(bucket.views, grads):
+        if g is not None:
+            v.copy_(g)
+    bucket.allreduce(world_size, group=group)
+    return bucket.flat
 
 
 def clip_grad_norm(params: Sequence[torch.nn.Parameter], max_norm: float = 0.5) -> float:
-    """gradient_clip_val 0.5 by norm (ddpm.py:607 / Lightning trainer)."""
+    """gradient_clip_val 0.5 by norm (ddpm.py:607 / Lightning trainer) over p.grad; one norm kernel per tensor but a
+    single host read."""
     grads = [p.grad for p in params if p.grad is not None]
-    total = math.sqrt(sum(float(g.float().pow(2).sum()) for g in grads))
-    scale = max_norm / (total + 1e-6)
-    if scale < 1:
-        for g in grads:
-            g.mul_(scale)
-    return total
+    if not grads:
+        return 0.0
+    total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g.float()) for g in grads]))
+    scale = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    for g in grads:
+        g.mul_(scale.to(g.dtype))
+    return float(total)
 
 
 class _QSampleOnly:
@@ -356,7 +397,64 @@ class DistillStep:
         eps = unet_forward_train(self.unet, self.q_sample(x0, t, noise), t, c, dict(self.extra_info))
         return distill_loss(eps, teacher_eps)
 
+    def micro_backward(self, batch: Dict[str, torch.Tensor], accum: int = 1, use_graph: bool = False) -> torch.Tensor:
+        """loss / accum backpropagated into the trainable parameters' .grad; returns the detached loss (no host sync).
+        use_graph: UNet forward + backward-to-context replayed from one CUDA graph (train.GraphedUNetLoss)."""
+        x0, t, noise, face_embs, tokens = batch["x0"], batch["t"], batch["noise"], batch["face_embs"], batch["tokens"]
+        teacher_eps = batch.get("teacher_eps")
+        if teacher_eps is None:
+            teacher_eps = self.teacher_eps(x0, t, noise, face_embs)
+        if not use_graph:
+            loss = self.loss(x0, t, noise, teacher_eps, face_embs, tokens)
+            (loss / accum).backward()
+            return loss.detach()
+        from .train import GraphedUNetLoss
+        c = self.context(face_embs, tokens)
+        g = self.__dict__.setdefault("_graphed", GraphedUNetLoss(self.unet, self.extra_info))
+        loss, grad_c = g(self.q_sample(x0, t, noise), t, c.detach(), teacher_eps)
+        c.backward(grad_c * (1.0 / accum))
+        return loss
+
     def micro_step(self, batch: Dict[str, torch.Tensor], accum: int = 1) -> float:
         loss = self.loss(batch["x0"], batch["t"], batch["noise"], batch.get("teacher_eps"), batch["face_embs"], batch["tokens"])
         (loss / accum).backward()
         return float(loss.detach())
+
+
+class Stage1Trainer:
+    """One optimizer step of the Stage-1 distillation (training_step ddpm.py:595-633 around guided_denoise :2483-2532):
+    `accum` micro-batches -> gradients accumulate in the flat bucket -> one all-reduce (mean over ranks) -> clip by norm
+    0.5 -> Prodigy (ldm/prodigy.py) on the same bucket.  The frozen UNet's forward + backward-to-context runs as one
+    CUDA graph per micro-batch geometry (train.GraphedUNetLoss) unless use_graph=False."""
+
+    def __init__(self, step: "DistillStep", params: Sequence[torch.nn.Parameter], world_size: int = 1, group=None,
+                 accum: int = 2, max_grad_norm: float = 0.5, optimizer=None, use_graph: bool = True):
+        from .prodigy import Prodigy
+        self.step, self.world_size, self.group = step, world_size, group
+        self.accum, self.max_grad_norm = accum, max_grad_norm
+        self.bucket = GradBucket(params)
+        self.optimizer = optimizer if optimizer is not None else Prodigy(self.bucket.params)
+        self.use_graph = use_graph
+        self.allreduce_ms = None
+
+    def optimizer_step(self, batches: Sequence[Dict[str, torch.Tensor]], time_allreduce: bool = False):
+        """-> {"loss": 0-d tensor (mean over the micro-batches), "grad_norm": 0-d tensor (before clipping)}."""
+        if len(batches) != self.accum:
+            raise ValueError(f"expected {self.accum} micro-batches, got {len(batches)}")
+        self.bucket.begin_step()
+        loss_sum = None
+        for b in batches:
+            li = self.step.micro_backward(b, accum=self.accum, use_graph=self.use_graph)
+            loss_sum = li if loss_sum is None else loss_sum + li
+        if time_allreduce and self.world_size > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.bucket.allreduce(self.world_size, group=self.group)
+            e1.record()
+            e1.synchronize()
+            self.allreduce_ms = e0.elapsed_time(e1)
+        else:
+            self.bucket.allreduce(self.world_size, group=self.group)
+        gn = self.bucket.clip_(self.max_grad_norm)
+        self.optimizer.step(self.bucket.flat)
+        return {"loss": loss_sum / self.accum, "grad_norm": gn}

@@ -406,6 +406,13 @@ class UNetModel(PackedModule):
     def res_blocks(self):
         return [m for m in self.modules() if isinstance(m, ResBlock)]
 
+    def _param_key(self):
+        # only the parameters this module packs itself (the sub-modules key their own packs)
+        srcs = [*self.time_embed.parameters(), *self.out.parameters()]
+        for rb in self.res_blocks():
+            srcs += [rb.emb_layers[1].weight, rb.emb_layers[1].bias]
+        return tuple((p.data_ptr(), p._version) for p in srcs)
+
     def _pack(self):
         f = lambda t: t.detach().float().contiguous()
         rbs = self.res_blocks()

@@ -171,8 +171,9 @@ int af_softmax_rows(const float* x, long long ldx, long long rows, int n, float 
 int af_upsample2x_cast(const float* x_nhwc, void* y_bf16, int B, int H, int W, int C, af_stream_t stream);
 
 /* CFG combine + DDIM update (ddim.py:260,279,283,295), reference fp32 operation order.
- * coef_table rows of 8 floats [g, sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma*temp, 0, 0];
- * row = *step_idx (device) or 0 when step_idx is NULL.  eps = [cond ; uncond] when has_uncond. */
+ * coef_table rows of 8 floats [g, sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma, temperature, 0]
+ * (the noise term is (sigma * noise) * temperature, ddim.py:286); row = *step_idx (device) or 0 when step_idx is NULL.
+ * eps = [cond ; uncond] when has_uncond.  x and x_prev may be the same buffer. */
 int af_cfg_ddim_update(const float* x, const float* eps, int has_uncond, const float* noise, const float* coef_table,
                        const int* step_idx, float* x_prev, float* pred_x0, long long n, af_stream_t stream);
 int af_advance_step(int* step_idx, const float* t_table, float* t_buf, int B, int num_steps, af_stream_t stream);

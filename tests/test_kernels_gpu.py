@@ -378,6 +378,34 @@ def test_cfg_ddim_update_bit_exact():
     assert torch.equal(xp.cpu(), ref)
 
 
+def test_cfg_ddim_update_stochastic_bit_exact_in_place():
+    """eta > 0, temperature != 1: noise term (sigma * noise) * temperature in the reference's order (ddim.py:286-295);
+    the graph path's in-place form (x_prev aliases x) gives the same bits."""
+    from adaprompt_b200 import ops
+    b = 2
+    x = _rand(b, 4, 32, 32, seed=4)
+    eps = _rand(2 * b, 4, 32, 32, seed=5)
+    noise = _rand(b, 4, 32, 32, seed=6)
+    a_t, a_prev, g, sigma, temp = torch.tensor(0.4123), torch.tensor(0.4788), 2.25, torch.tensor(0.1371), 0.85
+    s1m = torch.sqrt(1 - a_t)
+    coef = torch.tensor([[g, s1m.item(), a_t.sqrt().item(), a_prev.sqrt().item(), (1. - a_prev - sigma ** 2).sqrt().item(),
+                          sigma.item(), temp, 0]], dtype=torch.float32, device=DEV)
+    xp, p0 = torch.empty_like(x), torch.empty_like(x)
+    ops.cfg_ddim_update(x, eps, coef, xp, p0, has_uncond=True, noise=noise)
+    xc, ec, nc = x.cpu(), eps.cpu(), noise.cpu()
+    e_t, e_u = ec.chunk(2)
+    e = e_u + g * (e_t - e_u)
+    full = lambda v: torch.full((b, 1, 1, 1), float(v))
+    pred = (xc - full(s1m) * e) / full(a_t).sqrt()
+    dir_xt = (1. - full(a_prev) - full(sigma) ** 2).sqrt() * e
+    ref = full(a_prev).sqrt() * pred + dir_xt + full(sigma) * nc * temp
+    assert torch.equal(p0.cpu(), pred)
+    assert torch.equal(xp.cpu(), ref)
+    x2 = x.clone()
+    ops.cfg_ddim_update(x2, eps, coef, x2, p0, has_uncond=True, noise=noise)
+    assert torch.equal(x2, xp)
+
+
 # ------------------------------------------------------------------------------------------------ fused GN statistics
 def _group_stats_ref(x, eps):
     """x fp32 [B, HW, C] -> (mean, rstd) [B, 32] in float64."""

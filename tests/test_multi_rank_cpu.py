@@ -87,8 +87,12 @@ def _grad_worker(rank, world, port, out_dir):
     params = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
     g = torch.Generator().manual_seed(100 + rank)
     params[0].grad = torch.randn(5, 3, generator=g)
-    params[1].grad = torch.randn(7, generator=g)          # params[2] has no gradient on any rank: skipped
+    params[1].grad = torch.randn(7, generator=g)          # params[2] has no gradient on any rank: zeros in the bucket
+    if rank == 1:
+        params[1].grad = None                             # ... and params[1] none on rank 1: the bucket size must not change
     flat = allreduce_gradients(params, world)
+    for p_, o in zip(params, (0, 64, 128)):              # flat_layout(): 64-element aligned starts
+        p_.grad = flat[o:o + p_.numel()].view(p_.shape)
     total = clip_grad_norm(params, 0.5)
     torch.save({"g0": params[0].grad, "g1": params[1].grad, "flat": flat, "total": total}, os.path.join(out_dir, f"g{rank}.pt"))
     dist.destroy_process_group()
@@ -101,10 +105,45 @@ def test_world2_gloo_gradient_allreduce_is_the_mean(tmp_path):
     gens = [torch.Generator().manual_seed(100 + r) for r in range(world)]
     g0 = [torch.randn(5, 3, generator=g) for g in gens]
     g1 = [torch.randn(7, generator=g) for g in gens]
+    g1[1] = torch.zeros(7)
     m0, m1 = sum(g0) / world, sum(g1) / world
     total = float(torch.cat([m0.reshape(-1), m1.reshape(-1)]).norm())
     scale = min(1.0, 0.5 / (total + 1e-6))
     for r in range(world):
         o = torch.load(os.path.join(str(tmp_path), f"g{r}.pt"))
-        assert o["flat"].numel() == 22 and abs(o["total"] - total) < 1e-5
+        assert o["flat"].numel() == 192 and abs(o["total"] - total) < 1e-5     # fixed size on every rank (3 aligned slots)
         assert torch.allclose(o["g0"], m0 * scale, atol=1e-6) and torch.allclose(o["g1"], m1 * scale, atol=1e-6)
+
+
+def _bucket_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from adaprompt_b200.train_cond import GradBucket
+    w = torch.nn.Parameter(torch.ones(4, 3))
+    b = torch.nn.Parameter(torch.zeros(3))
+    unused = torch.nn.Parameter(torch.zeros(2))
+    bucket = GradBucket([w, b, unused])
+    bucket.begin_step()
+    x = torch.arange(8.0).reshape(2, 4) + rank
+    for _ in range(2):                                   # two accumulated micro-batches
+        ((x @ w + b).sum() / 2).backward()
+    assert w.grad.data_ptr() == bucket.views[0].data_ptr()          # autograd accumulated IN the bucket
+    work = bucket.allreduce(world, async_op=True)
+    bucket.wait()
+    total = bucket.clip_(0.5)
+    torch.save({"flat": bucket.flat.clone(), "total": float(total)}, os.path.join(out_dir, f"b{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_grad_bucket_accumulates_allreduces_and_clips(tmp_path):
+    world = 2
+    mp.spawn(_bucket_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    gw = sum((torch.arange(8.0).reshape(2, 4) + r).sum(0)[:, None].expand(4, 3) for r in range(world)) / world
+    gb = torch.full((3,), 2.0)
+    ref = torch.zeros(192)
+    ref[:12], ref[64:67] = gw.reshape(-1), gb
+    scale = min(1.0, 0.5 / (float(ref.norm()) + 1e-6))
+    for r in range(world):
+        o = torch.load(os.path.join(str(tmp_path), f"b{r}.pt"))
+        assert abs(o["total"] - float(ref.norm())) < 1e-4
+        assert torch.allclose(o["flat"], ref * scale, atol=1e-6)

@@ -430,6 +430,63 @@ def test_distill_step_end_to_end_gradients():
     assert worst[1] < 8e-2, worst
 
 
+def test_stage1_trainer_graph_matches_eager_and_steps_the_optimizer():
+    """Stage1Trainer: (1) the CUDA-graph replay of the UNet forward + backward-to-context leaves the same gradient bucket
+    as the eager tape (same kernels, same order: rel-L2 < 1e-5), twice in a row (replay with new inputs); (2) the bucket
+    is what Prodigy consumes: the weights move, and the version-keyed packs of the inference mirror see the new
+    weights (a stale bf16 pack after an optimizer step)."""
+    from adaprompt_b200.train_cond import DistillStep, Stage1Trainer, trainable_parameters
+    from oracle import text_oracle as to
+    from oracle.unet_oracle import make_alphas_cumprod
+    from test_text_gpu import StubTokenizer
+    unet, _ = _unet()
+    sbg, _ = _sbg_small(31, 2)
+    frozen, _ = _clip_small(32, 2)
+    arc2face, _ = _clip_small(33, 2)
+    frozen.text_model.last_layers_skip_weights = [0.5, 0.5]
+    for m in (frozen, arc2face):
+        for p in m.parameters():
+            p.requires_grad = False
+    acp = torch.tensor(make_alphas_cumprod(), dtype=torch.float32)
+    step = DistillStep(unet, frozen.text_model, sbg, arc2face.eval(), StubTokenizer(), acp, to.TOK_Z)
+    params = trainable_parameters(sbg)
+    g = torch.Generator().manual_seed(19)
+
+    def batch():
+        B = 2
+        return {k: v.cuda() for k, v in {
+            "x0": torch.randn(B, 4, 32, 32, generator=g), "noise": torch.randn(B, 4, 32, 32, generator=g),
+            "t": torch.randint(0, 1000, (B,), generator=g), "teacher_eps": torch.randn(B, 4, 32, 32, generator=g),
+            "face_embs": F.normalize(torch.randn(B, 512, generator=g), dim=-1),
+            "tokens": torch.tensor([to.subject_prompt_ids(77)] * B)}.items()}
+
+    class NoOpt:
+        def step(self, flat):
+            self.seen = flat.clone()
+
+    eager = Stage1Trainer(step, params, accum=2, use_graph=False, optimizer=NoOpt())
+    graph = Stage1Trainer(step, params, accum=2, use_graph=True, optimizer=NoOpt())
+    for rep in range(2):
+        bs = [batch(), batch()]
+        o_e = eager.optimizer_step(bs)
+        o_g = graph.optimizer_step(bs)
+        assert _rel(graph.optimizer.seen, eager.optimizer.seen) < 1e-5, rep
+        assert abs(float(o_e["loss"]) - float(o_g["loss"])) < 1e-6 * abs(float(o_e["loss"])) + 1e-7
+        assert float(o_g["grad_norm"]) > 0 and float(graph.optimizer.seen.norm()) <= 0.5 + 1e-4      # clipped to 0.5
+    # the real optimizer on the same bucket
+    trainer = Stage1Trainer(step, params, accum=2, use_graph=True)
+    w = sbg.prompt2token_proj.text_model.encoder.layers[0].mlp.fc1.weight
+    layer = sbg.prompt2token_proj.text_model.encoder.layers[0]
+    pack_before = layer.packed()["w1"].clone()
+    w_before = w.detach().clone()
+    for _ in range(3):
+        trainer.optimizer_step([batch(), batch()])
+    assert trainer.optimizer.param_groups[0]["k"] == 3
+    assert not torch.equal(w.detach(), w_before)
+    assert torch.equal(layer.packed()["w1"], w.detach().to(torch.bfloat16))          # repacked from the moved weights
+    assert not torch.equal(layer.packed()["w1"], pack_before)
+
+
 # ------------------------------------------------------------------------------------------------ optimizer
 @pytest.mark.parametrize("case", ["default", "decay_biascorr", "coupled_decay_growth"])
 def test_prodigy_matches_reference_golden(case):
