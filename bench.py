@@ -86,6 +86,15 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(world: int, graph: bool = True):
+    b = IMAGES_PER_GPU
+    return {"workload": "ddim50_cfg_512px_batch8_per_gpu", "ddim_steps": DDIM_STEPS, "images_per_gpu": b,
+            "unet_batch": 2 * b, "guidance_scale": list(GUIDANCE), "eta": 0.0, "latent": [4, LATENT, LATENT],
+            "context": [16 * b, 77, 768], "parallelism": f"dp{world}",
+            "weights": "random-init SD-1.5 architecture (seed 1234)",
+            "l2": "activations per UNet step (>1 GB) exceed the 126 MB L2; no explicit flush", "cuda_graph": graph}
+
+
 def cpu_oracle_pair_seconds(reps: int, warmup: int):
     """Times the CPU oracle (oracle/unet_oracle.py, fp32) on ONE CFG pair (UNet batch 2, 64x64 latent)."""
     import torch
@@ -113,8 +122,9 @@ def cpu_oracle_pair_seconds(reps: int, warmup: int):
 
 def run_reference(args):
     """--impl reference: the reference algorithm (fp32 oracle port of UNetModel + DDIM/CFG arithmetic) on the host
-    cores.  Each step is a bounded sample of the workload: one CFG-pair UNet evaluation; a 512^2 DDIM-50 image
-    costs 50 of them, so images/s = 1 / (50 * t_pair)."""
+    cores.  Each step is a bounded sample of the workload: one CFG-pair UNet evaluation (UNet batch 2 = one image's
+    denoising step); a 512^2 DDIM-50 image costs 50 of them, so images/s = 1 / (50 * t_pair) - an EXTRAPOLATION from the
+    sample, stated in the line.  One host process whatever --gpus says: the value does not scale with N."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -124,14 +134,127 @@ def run_reference(args):
         "impl": "reference", "metric": "ddim50_cfg_512x512_images_per_sec", "value": value, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3 * DDIM_STEPS * IMAGES_PER_GPU,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ddim50_cfg_512px_batch8_per_gpu", "ddim_steps": DDIM_STEPS, "guidance_scale": list(GUIDANCE),
-                   "latent": [4, LATENT, LATENT], "weights": "random-init SD-1.5 architecture (seed 1234)"},
+        "config": workload_config(1, graph=False),
+        "extrapolated": True, "host_processes": 1,
+        "note": "one CPU process regardless of --gpus (rank 0 only): a ratio against an N-GPU line compares N GPUs with "
+                "one host process",
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{len(times)} x one CFG-pair UNet forward (batch 2, 64x64 latent, fp32), "
-                                   f"median {med:.2f} s; x50 steps per image"},
+                         "sample": f"{len(times)} x one CFG-pair UNet forward (UNet batch 2 of the 16, 64x64 latent, fp32), "
+                                   f"median {med:.2f} s; x50 DDIM steps per image (extrapolated)"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def gpu_oracle_legs(dev, unet, sampler_call, dev_in, extra, b):
+    """Parity gate + practical GPU baseline, both with the fp32 oracle port of the reference
+    path (oracle/unet_oracle.py: plain torch functional ops -> cuDNN / cuBLAS eager kernels) on the SAME GPU:
+      parity: eps of the timed batch-16 UNet step for one conditional and one unconditional sample, and the final latent
+              of image 0 of the timed 50-step run, against the oracle with TF32 off (budgets 1e-2 / 2e-2, north_star);
+      gpu_eager_baseline: the oracle's UNet step at batch 16 in fp32 (torch defaults), under bf16 and fp16 autocast."""
+    import torch
+    from adaprompt_b200.weights import synth_state_dict
+    from oracle.golden_inputs import EXTRA_INFO
+    from oracle.unet_oracle import UNetSpec, ddim_sample, unet_forward
+    spec = UNetSpec()
+    sd = {k: v.to(dev) for k, v in synth_state_dict(spec.state_spec(), 1234).items()}
+    rel = lambda a, r: float((a.float() - r.float()).norm() / r.float().norm())
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    x_in = torch.cat([dev_in[2]] * 2)
+    t_in = torch.full((2 * b,), 501.0, device=dev)
+    c2 = torch.cat([dev_in[0], dev_in[1]])
+    out = {}
+    with torch.no_grad():
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        eps = unet(x_in, t_in, context=c2, extra_info=dict(extra))
+        idx = [0, b]                                       # one conditional, one unconditional sample of the batch
+        ctx = torch.cat([c2[16 * i:16 * (i + 1)] for i in idx])
+        ref = unet_forward(sd, spec, x_in[idx], t_in[idx].long(), ctx, dict(EXTRA_INFO))
+        eps_err = [rel(eps[i], ref[k]) for k, i in enumerate(idx)]
+        lat = sampler_call(*dev_in)                        # the timed call, once more
+        cond = (dev_in[0][:16], ["p"], dict(EXTRA_INFO))
+        uncond = (dev_in[1][:16], [""], dict(EXTRA_INFO))
+        apply = lambda x, t, c: unet_forward(sd, spec, x, t, c[0], dict(c[2]))
+        ref_lat, _ = ddim_sample(apply, DDIM_STEPS, [1, 4, LATENT, LATENT], cond, uncond, GUIDANCE, dev_in[2][:1])
+        lat_err = rel(lat[0], ref_lat[0])
+        out["parity"] = {"eps_rel_l2": {"cond_sample_0": eps_err[0], f"uncond_sample_{b}": eps_err[1]}, "eps_budget": 1e-2,
+                         "final_latent_rel_l2_image0": lat_err, "latent_budget": 2e-2,
+                         "ok": bool(max(eps_err) < 1e-2 and lat_err < 2e-2),
+                         "against": "fp32 oracle port (oracle/unet_oracle.py, pinned to the unmodified reference by "
+                                    "tests/golden) in eager torch on this GPU, TF32 off"}
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+
+        def time_step(autocast_dtype):
+            def run():
+                if autocast_dtype is None:
+                    return unet_forward(sd, spec, x_in, t_in.long(), c2, dict(EXTRA_INFO))
+                with torch.autocast("cuda", dtype=autocast_dtype):
+                    return unet_forward(sd, spec, x_in, t_in.long(), c2, dict(EXTRA_INFO))
+            run()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); run(); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            return sorted(ts)[1]
+
+        base = {"fp32_ms": time_step(None), "bf16_autocast_ms": time_step(torch.bfloat16),
+                "fp16_autocast_ms": time_step(torch.float16)}
+        base.update({"unit": "ms per UNet step, batch 16, 64x64 latent", "kind": "port",
+                     "what": "oracle port of the reference modules (same torch ops the reference issues: F.conv2d, "
+                             "F.linear, einsum attention with the [B*8, N, N] scores materialised, F.group_norm) run "
+                             "eagerly on this B200 through cuDNN / cuBLAS; fp16 autocast is the reference CLI's default "
+                             "(scripts/stable_txt2img.py:179-184,614)"})
+        out["gpu_eager_baseline"] = base
+    del sd
+    torch.cuda.empty_cache()
+    return out
+
+
+def train_leg(dev, unet, world, rank, steps):
+    """Stage-1 distillation (BASELINE.json configs[3]) through train_cond.Stage1Trainer: per GPU 4 x 2 accumulation
+    micro-batches at 64x64 latents, one NCCL all-reduce of the gradient bucket per optimizer step, clip 0.5, Prodigy."""
+    import torch
+    import torch.distributed as dist
+    from adaprompt_b200.synthetic import stage1_batch, stage1_stack
+    from adaprompt_b200.train_cond import Stage1Trainer
+    step, params = stage1_stack(dev, unet=unet)
+    trainer = Stage1Trainer(step, params, world_size=world, accum=2)
+    g = torch.Generator().manual_seed(100 + rank)
+    batches = lambda: [stage1_batch(dev, 4, LATENT, g) for _ in range(2)]
+    for _ in range(2):
+        trainer.optimizer_step(batches())
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = trainer.optimizer_step(batches())
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    trainer.optimizer_step(batches(), time_allreduce=True)
+    ms_step = float(ms) / steps
+    n_params = sum(p.numel() for p in params)
+    info = {"metric": "stage1_distill_samples_per_sec", "value": world * 8 / (ms_step / 1e3), "unit": "samples/s",
+            "ms_per_optimizer_step": ms_step, "optimizer_steps": steps, "allreduce_ms": trainer.allreduce_ms,
+            "allreduce_bytes_per_step": 4 * trainer.bucket.flat.numel() if world > 1 else 0,
+            "collective": "one NCCL all-reduce (SUM -> mean) of the flat fp32 gradient bucket per optimizer step" if world > 1 else None,
+            "trainable_params": n_params, "loss": float(out["loss"]), "grad_norm": float(out["grad_norm"]),
+            "config": {"workload": "stage1_distill_bs4x2accum_64x64", "micro_batch": 4, "grad_accum": 2,
+                       "optimizer": "Prodigy", "clip_grad_norm": 0.5, "unet_cuda_graph": True,
+                       "teacher_eps": "fixed random tensor (SURVEY.md 8(d) config 4)"}}
+    del trainer, step, params
+    torch.cuda.empty_cache()
+    return info
 
 
 def main():
@@ -144,6 +267,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-vae", action="store_true", help="skip the sampling + first-stage-decoder leg (vae_decode key)")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel-class table to stderr")
+    ap.add_argument("--no-train", action="store_true", help="skip the Stage-1 training leg (train_step key)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity gate / GPU eager baseline legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -301,13 +426,15 @@ def main():
         d = breakdown[dom]
         achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01_unet_step_traffic.json")   # one ncu pass of the same UNet step
+        tpath = os.path.join(ROOT, "profiles", "r02_unet_step_traffic.json")   # one ncu pass of the same UNet step
+        if not os.path.exists(tpath):
+            tpath = os.path.join(ROOT, "profiles", "r01_unet_step_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath)).get(dom)
             if tj and tj["launches"]:
                 traffic = tj["dram_bytes"] / tj["launches"]
-                traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu pass of scripts/unet_step.py "
-                               f"(profiles/r01_unet_step_traffic.json; algorithmic {tj['algorithmic_bytes'] / tj['launches']:.3e} B)")
+                traffic_src = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu pass of scripts/unet_step.py "
+                               f"({os.path.relpath(tpath, ROOT)}; algorithmic {tj['algorithmic_bytes'] / tj['launches']:.3e} B)")
         roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"],
                     "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
                     "traffic_source": traffic_src,
@@ -315,11 +442,23 @@ def main():
                     "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
                     "share_of_unet_step": d["ms"] / step_ms,
                     "how": "CUDA events around every launch of one eager UNet step (batch 16, t=501)"}
-        gn = breakdown.get("af_groupnorm_silu")
-        if gn:
-            gbs = gn["bytes"] / (gn["ms"] * 1e-3) / 1e9
+        gn_parts = [breakdown[n] for n in ("af_groupnorm_silu", "af_groupnorm_apply", "af_groupnorm_finalize",
+                                           "af_groupnorm_stats") if n in breakdown]
+        if gn_parts:
+            # the whole GroupNorm class: apply + finalize + stats launches; bytes = 6 per element (fp32 in, bf16 out),
+            # charged once (to the apply pass); also reported against the 4 B/element of a bf16-in / bf16-out norm
+            gn_ms = sum(v["ms"] for v in gn_parts)
+            gn_bytes = sum(v["bytes"] for v in gn_parts)
+            gbs = gn_bytes / (gn_ms * 1e-3) / 1e9
+            ap_ = breakdown.get("af_groupnorm_apply") or breakdown.get("af_groupnorm_silu")
+            big = prof.by_shape.get(f"groupnorm_apply B{2 * b} HW{LATENT * LATENT} C320")
             roofline["groupnorm_silu"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                          "frac": gbs / peaks["hbm_gbs"], "share_of_unet_step": gn["ms"] / step_ms}
+                                          "frac": gbs / peaks["hbm_gbs"], "share_of_unet_step": gn_ms / step_ms,
+                                          "launches": sum(v["launches"] for v in gn_parts), "ms": gn_ms,
+                                          "bytes_per_element": 6,
+                                          "frac_at_4_bytes_per_element": gbs * 4 / 6 / peaks["hbm_gbs"],
+                                          "apply_pass_only_gbs": ap_["bytes"] / (ap_["ms"] * 1e-3) / 1e9 if ap_ else None,
+                                          "apply_64x64_c320_gbs": big["bytes"] / (big["ms"] * 1e-3) / 1e9 if big else None}
         at = breakdown.get("af_attention_bf16")
         if at:
             tf = at["flops"] / (at["ms"] * 1e-3) / 1e12
@@ -338,6 +477,19 @@ def main():
                 gb = v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0
                 print(f"  {n:52s} x{v['launches']:3d} {v['ms']:8.3f} ms  {tf:7.1f} TF/s {gb:7.1f} GB/s", file=sys.stderr)
 
+    # ---- parity gate + practical GPU baseline (rank 0) -------------------------------------------------------
+    oracle_legs = {}
+    if rank == 0 and not args.no_parity:
+        oracle_legs = gpu_oracle_legs(dev, unet, one_call, dev_in, extra, b)
+
+    # ---- Stage-1 training leg (all ranks: its gradient all-reduce is the one data-path collective) ------------
+    train_info = None
+    if not args.no_train:
+        sampler.__dict__.pop("_step_graphs", None)
+        sampler._graphs = {}
+        torch.cuda.empty_cache()
+        train_info = train_leg(dev, unet, world, rank, max(2, args.steps))
+
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample ---------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -352,12 +504,7 @@ def main():
             "metric": "ddim50_cfg_512x512_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "ddim50_cfg_512px_batch8_per_gpu", "ddim_steps": DDIM_STEPS,
-                       "images_per_gpu": b, "unet_batch": 2 * b, "guidance_scale": list(GUIDANCE), "eta": 0.0,
-                       "latent": [4, LATENT, LATENT], "context": [16 * b, 77, 768], "parallelism": f"dp{world}",
-                       "weights": "random-init SD-1.5 architecture (seed 1234)",
-                       "l2": "activations per UNet step (>1 GB) exceed the 126 MB L2; no explicit flush",
-                       "cuda_graph": not args.no_graph},
+            "config": workload_config(world, graph=not args.no_graph),
             "unet_step_ms": ms_per_step / DDIM_STEPS,
             "unet_tflops_algorithmic": unet_tflops,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -367,6 +514,9 @@ def main():
             "clocks": clock_info,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "parity": oracle_legs.get("parity"),
+            "gpu_eager_baseline": oracle_legs.get("gpu_eager_baseline"),
+            "train_step": train_info,
         }
         print(json.dumps(line))
     if world > 1:

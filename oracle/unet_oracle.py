@@ -146,7 +146,7 @@ class UNetSpec:
 def timestep_embedding(timesteps: torch.Tensor, dim: int, max_period: int = 10000) -> torch.Tensor:
     """ldm/modules/diffusionmodules/util.py:154-174 (cos first, then sin)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(timesteps.device)
     args = timesteps[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:
@@ -326,7 +326,7 @@ def ddim_sample(apply_model, S: int, shape, cond, uncond, guidance_scale, x_T: t
     gs = guidance_schedule(S, guidance_scale)
     for i, step in enumerate(np.flip(ts)):
         index = S - i - 1
-        t = torch.full((b,), int(step), dtype=torch.long)
+        t = torch.full((b,), int(step), dtype=torch.long, device=img.device)
         g = gs[i]
         if uncond is None or g == 1.0:
             e_t = apply_model(img, t, cond)
@@ -336,13 +336,11 @@ def ddim_sample(apply_model, S: int, shape, cond, uncond, guidance_scale, x_T: t
             c2 = (torch.cat([c_c, c_u]), sum([c_in_c, c_in_u], []), extra)
             e_t, e_u = apply_model(torch.cat([img] * 2), torch.cat([t] * 2), c2).chunk(2)
             e_t = e_u + g * (e_t - e_u)
-        a_t = torch.full((b, 1, 1, 1), alphas[index])
-        a_prev = torch.full((b, 1, 1, 1), alphas_prev[index])
-        sigma_t = torch.full((b, 1, 1, 1), sigmas[index])
-        s1m_t = torch.full((b, 1, 1, 1), s1m[index])
+        full = lambda v: torch.full((b, 1, 1, 1), float(v), device=img.device)
+        a_t, a_prev, sigma_t, s1m_t = full(alphas[index]), full(alphas_prev[index]), full(sigmas[index]), full(s1m[index])
         pred_x0 = (img - s1m_t * e_t) / a_t.sqrt()
         dir_xt = (1. - a_prev - sigma_t ** 2).sqrt() * e_t
-        noise = sigma_t * torch.randn(img.shape, generator=generator)
+        noise = sigma_t * torch.randn(img.shape, generator=generator, device=img.device)
         img = a_prev.sqrt() * pred_x0 + dir_xt + noise
         if index % log_every_t == 0 or index == S - 1:
             inter["x_inter"].append(img)
