@@ -499,6 +499,42 @@ class UNetModel(PackedModule):
             cache.pop(0)
         return kvs
 
+    def compel_context_kv(self, context, B, iter_type, empty_context, prob, level_or_range, is_training):
+        """Compel-style CFG on the context (openaimodel.py:898-916 + ldm/util.py:1823-1854): per cross-attention layer, with
+        probability `prob`, ctx <- (ctx - empty) * 1.1**level + empty on the instances the batch mask selects (inference:
+        the first half of the batch; training: all, or - at 50 % - the second half only).  The draws come from Python's
+        global `random` in exactly the reference's order (per layer: [training: mask coin,] gate, level, and one more
+        gate draw per element of the (v, k) tuple), so a seeded run reproduces the reference.  Nothing is cached: the
+        K / V projections are recomputed from the re-weighted context on every forward."""
+        import random
+        ctx = context.reshape(B, 16, -1, context.shape[-1]).permute(1, 0, 2, 3)
+        kvs = {}
+        for layer_idx, attn2 in self._ca_modules().items():          # ascending layer order, as the forward visits them
+            c = ctx[L2CA[layer_idx]].float().contiguous()
+            v_c, k_c = (t.contiguous() for t in c.chunk(2, dim=1)) if iter_type == "mix_hijk" else (c, c)
+            mask = torch.ones(B, dtype=torch.float32, device=c.device)
+            if is_training:
+                if random.random() < 0.5:
+                    mask[:B // 2] = 0
+            else:
+                mask[B // 2:] = 0
+            if not (empty_context is None or level_or_range is None or random.random() > prob):
+                level = random.uniform(*level_or_range) if isinstance(level_or_range, (list, tuple)) else level_or_range
+                w = 1.1 ** level
+                e = empty_context.to(c.device).float()
+                m = mask.reshape(-1, 1, 1)
+
+                def reweight(t):
+                    random.random()                                    # the recursive call's own (always passing) gate
+                    t2 = (t - e) * w + e
+                    return (t2 * m + t * (1 - m)).contiguous()
+
+                v_c, k_c = reweight(v_c), reweight(k_c)                 # tuple order (v, k): ldm/util.py:1837
+            kv = attn2.project_context(k_c, v_c)
+            attn2.__dict__["_kv_cache"] = None
+            kvs[layer_idx] = kv
+        return kvs
+
     # ------------------------------------------------------------------ forward
     def time_embedding(self, timesteps: torch.Tensor):
         """-> (emb [B, 4*mc] fp32, emb_rows [B, sum Cout] = every ResBlock's emb_layers(emb))."""
@@ -542,10 +578,12 @@ class UNetModel(PackedModule):
             raise ValueError("extra_info['use_layerwise_context'] must be True")
         if capture_distill_attn or debug_attn:
             raise NotImplementedError("capture_distill_attn / debug_attn (training-time attention capture)")
-        if apply_compel_cfg_prob > 0:
-            raise NotImplementedError("compel-style CFG on the context (apply_compel_cfg_prob > 0)")
         B = x.shape[0]
-        kvs = self.context_kv(context, B, iter_type)
+        if apply_compel_cfg_prob > 0:
+            kvs = self.compel_context_kv(context, B, iter_type, ei.get("empty_context", None), apply_compel_cfg_prob,
+                                         ei.get("compel_cfg_weight_level_range", None), is_training)
+        else:
+            kvs = self.context_kv(context, B, iter_type)
 
         # flag side channel (openaimodel.py:922-945, restored at :1041-1045)
         sizes = np.ones(16, dtype=int) * use_conv_attn_kernel_size

@@ -40,6 +40,21 @@ def unet_inputs(name: str):
         mask[:, :, :2] = 1.0
         extra["img_mask"] = mask
         return x, torch.full((1,), 261, dtype=torch.long), ctx, extra
+    if name == "b16_t501_64":          # the benchmarked UNet batch (8 images x [cond ; uncond]) at 64x64
+        g = _g(11)
+        return torch.randn(16, 4, 64, 64, generator=g), torch.full((16,), 501, dtype=torch.long), \
+            torch.randn(256, 77, 768, generator=g), extra
+    if name == "b2_t741_hijk_32":      # iter_type mix_hijk (openaimodel.py:885-892): context = [v_ctx | k_ctx] along tokens
+        g = _g(12)
+        extra["iter_type"] = "mix_hijk"
+        return torch.randn(2, 4, 32, 32, generator=g), torch.tensor([741, 741]), \
+            torch.randn(32, 154, 768, generator=g), extra
+    if name == "b2_t341_compel_32":    # compel-style CFG on the context (openaimodel.py:898-916), inference batch mask
+        g = _g(13)
+        extra.update(apply_compel_cfg_prob=0.7, compel_cfg_weight_level_range=(1, 3),
+                     empty_context=torch.randn(1, 77, 768, generator=g), python_random_seed=1234)
+        return torch.randn(2, 4, 32, 32, generator=g), torch.tensor([341, 341]), \
+            torch.randn(32, 77, 768, generator=g), extra
     raise KeyError(name)
 
 
@@ -66,6 +81,8 @@ def ddim_inputs(name: str):
         g, S, hw = _g(31), 10, 32
     elif name == "s50_64_g4_1":
         g, S, hw = _g(32), 50, 64
+    elif name == "s50_32_g10_4":       # the CLI's default scale (stable_txt2img.py:152), x_inter logged at EVERY step
+        g, S, hw = _g(33), 50, 32
     else:
         raise KeyError(name)
     b = 1
@@ -74,4 +91,4 @@ def ddim_inputs(name: str):
     x_T = torch.randn(b, 4, hw, hw, generator=g)
     cond = (c, ["a photo of a z"] * b, dict(EXTRA_INFO))
     uncond = (uc, [""] * b, dict(EXTRA_INFO))
-    return S, (b, 4, hw, hw), cond, uncond, (4.0, 1.0), x_T
+    return S, (b, 4, hw, hw), cond, uncond, (10.0, 4.0) if name.endswith("g10_4") else (4.0, 1.0), x_T

@@ -46,11 +46,27 @@ def main():
     if cases:
         torch.save(cases, os.path.join(OUT, "unet_eps.pt"))
 
+    # ---- 1b. round-2 additions (own file: the round-1 fixtures stay byte-identical) --------------------
+    cases2 = {}
+    for name in () if (only and "unet2" not in only) else ("b16_t501_64", "b2_t741_hijk_32", "b2_t341_compel_32"):
+        x, t, ctx, extra = unet_inputs(name)
+        seed = extra.pop("python_random_seed", None)
+        if seed is not None:
+            import random
+            random.seed(seed)          # prob_apply_compel_cfg draws from Python's global generator (ldm/util.py:1826,1830)
+        t0 = time.time()
+        with torch.no_grad():
+            eps = unet(x, t, context=ctx, extra_info=extra)
+        cases2[name] = {"eps": eps.clone(), "x_sum": checksum(x), "ctx_sum": checksum(ctx)}
+        print(f"unet {name}: {time.time() - t0:.1f}s  |eps|={eps.abs().mean():.4f}")
+    if cases2:
+        torch.save(cases2, os.path.join(OUT, "unet_eps_r02.pt"))
+
     # ---- 2. module-level ---------------------------------------------------------------------------
     mods = {}
     mi = module_inputs()
     with torch.no_grad():
-      if not only or "modules" in only:
+      if (not only) or "modules" in only:
             rb = unet.output_blocks[5][0]           # ResBlock 1920 -> 1280 with 1x1 skip conv
             mods["res_out5"] = rb(mi["res_out5"]["x"], mi["res_out5"]["emb"])
             rb2 = unet.input_blocks[1][0]           # ResBlock 320 -> 320 identity skip
@@ -77,6 +93,21 @@ def main():
         torch.save({k: v.clone() for k, v in mods.items()}, os.path.join(OUT, "modules.pt"))
     print("modules done")
 
+    if only and "ddim2" in only:
+        name = "s50_32_g10_4"
+        S, shape, cond, uncond, gs, x_T = ddim_inputs(name)
+        model = rh.FakeLatentDiffusion(unet)
+        sampler = rh.cpu_ddim_sampler(model)
+        t0 = time.time()
+        with contextlib.redirect_stdout(io.StringIO()), torch.no_grad():
+            samples, inter = sampler.sample(S, shape[0], list(shape[1:]), conditioning=cond,
+                                            unconditional_conditioning=uncond, guidance_scale=gs, eta=0.0,
+                                            x_T=x_T, verbose=False, log_every_t=1)
+        torch.save({name: {"samples": samples.clone(), "x_inter": [t.clone() for t in inter["x_inter"]],
+                           "pred_x0": [t.clone() for t in inter["pred_x0"]], "calls": model.calls,
+                           "xT_sum": checksum(x_T)}}, os.path.join(OUT, "ddim_traj_r02.pt"))
+        print(f"ddim {name}: {time.time() - t0:.1f}s, {model.calls} UNet calls, {len(inter['x_inter'])} logged states")
+        return
     if "--skip-ddim" in sys.argv or (only and "ddim" not in only):
         return
     # ---- 3. DDIM trajectories ----------------------------------------------------------------------

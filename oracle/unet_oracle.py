@@ -241,12 +241,37 @@ def unet_forward(sd: SD, spec: UNetSpec, x: torch.Tensor, timesteps: torch.Tenso
     emb = F.linear(F.silu(emb), sd["time_embed.2.weight"], sd["time_embed.2.bias"])
     ctx = context.reshape(B, 16, -1, context.shape[-1]).permute(1, 0, 2, 3)  # :866
 
+    compel_prob = extra_info.get("apply_compel_cfg_prob", 0)
+    empty_ctx, compel_range = extra_info.get("empty_context", None), extra_info.get("compel_cfg_weight_level_range", None)
+    is_training = extra_info.get("is_training", True)
+
+    def compel(e, level, batch_mask, gate_prob):
+        """prob_apply_compel_cfg (ldm/util.py:1823-1854) on one tensor; draws from Python's global `random`."""
+        import random
+        if empty_ctx is None or level is None or random.random() > gate_prob:
+            return e
+        e2 = (e - empty_ctx) * (1.1 ** level) + empty_ctx
+        m = batch_mask.reshape(-1, 1, 1)
+        return e2 * m + e * (1 - m)
+
     def layer_ctx(layer_idx):
         c = ctx[LAYER2CA[layer_idx]]
         if iter_type == "mix_hijk":  # :885-892, (v, k) halves along the token dim
             v, k = c.chunk(2, dim=1)
-            return (v, k)
-        return (c, c)
+        else:
+            v = k = c
+        if compel_prob > 0:          # :898-916
+            import random
+            bm = torch.ones(B, dtype=torch.float32, device=x.device)
+            if is_training:
+                if random.random() < 0.5:
+                    bm[:B // 2] = 0
+            else:
+                bm[B // 2:] = 0
+            if not (empty_ctx is None or compel_range is None or random.random() > compel_prob):
+                level = random.uniform(*compel_range) if isinstance(compel_range, (list, tuple)) else compel_range
+                v, k = compel(v, level, bm, 1), compel(k, level, bm, 1)     # recursion over the (v, k) tuple, :1837
+        return (v, k)
 
     def run(prefix, layers, h, layer_idx):
         for j, l in enumerate(layers):

@@ -61,6 +61,44 @@ def test_unet_eps_vs_reference_golden(unet, name):
     assert err < EPS_TOL
 
 
+@pytest.mark.parametrize("name", ["b16_t501_64", "b2_t741_hijk_32", "b2_t341_compel_32"])
+def test_unet_eps_vs_reference_golden_round2(unet, name):
+    """The benchmarked configuration itself (UNet batch 16 at 64x64: cta_group::2 pair tiles on, 16-sample cross
+    attention), iter_type mix_hijk (v_ctx != k_ctx, openaimodel.py:885-896) and compel-style CFG on the context
+    (:898-916, seeded like the reference run) against the UNMODIFIED reference (oracle/make_golden.py --only=unet2)."""
+    import random
+    from oracle.golden_inputs import checksum, unet_inputs
+    gold = torch.load(os.path.join(GOLD, "unet_eps_r02.pt"))[name]
+    x, t, ctx, extra = unet_inputs(name)
+    seed = extra.pop("python_random_seed", None)
+    if seed is not None:
+        random.seed(seed)
+    assert abs(checksum(x) - gold["x_sum"]) < 1e-6 * gold["x_sum"]
+    assert abs(checksum(ctx) - gold["ctx_sum"]) < 1e-6 * gold["ctx_sum"]
+    with torch.no_grad():
+        eps = unet(x.cuda(), t.cuda(), context=ctx.cuda(), extra_info=_cuda_extra(extra))
+    errs = [_rel(eps[i], gold["eps"][i]) for i in range(eps.shape[0])]
+    print(f"unet eps {name}: rel-L2 {_rel(eps, gold['eps']):.3e}, worst sample {max(errs):.3e}")
+    assert max(errs) < EPS_TOL
+
+
+def test_unet_batch16_pair_mode_on_off_bit_identical(unet):
+    """cta_group::2 pair tiles (auto-enabled at batch 16) vs single-CTA tiles over the WHOLE UNet: same accumulation
+    order, so the eps must be bit-identical."""
+    from adaprompt_b200 import _lib
+    from oracle.golden_inputs import unet_inputs
+    x, t, ctx, extra = unet_inputs("b16_t501_64")
+    lib = _lib.load()
+    with torch.no_grad():
+        a = unet(x.cuda(), t.cuda(), context=ctx.cuda(), extra_info=_cuda_extra(extra)).clone()
+        old = lib.af_gemm_set_pair_mode(0)
+        try:
+            b = unet(x.cuda(), t.cuda(), context=ctx.cuda(), extra_info=_cuda_extra(extra)).clone()
+        finally:
+            lib.af_gemm_set_pair_mode(old)
+    assert torch.equal(a, b)
+
+
 def test_unet_eps_vs_oracle_fresh_inputs(unet, state_dict):
     """Oracle computed here on the box's CPU (32x32 latent keeps it to a few seconds)."""
     from oracle.golden_inputs import EXTRA_INFO
@@ -153,6 +191,24 @@ def test_ddim_trajectory_vs_reference_golden(unet, name):
     assert len(inter["x_inter"]) == len(gold["x_inter"])
     assert _rel(samples, gold["samples"]) < DDIM_TOL
     assert max(errs) < DDIM_TOL
+
+
+def test_ddim_trajectory_every_step_g10_4_vs_reference_golden(unet):
+    """(10 -> 4) guidance, 50 steps, every intermediate state (log_every_t = 1) against the unmodified reference sampler."""
+    from oracle.golden_inputs import ddim_inputs
+    name = "s50_32_g10_4"
+    gold = torch.load(os.path.join(GOLD, "ddim_traj_r02.pt"))[name]
+    S, shape, cond, uncond, gs, x_T = ddim_inputs(name)
+    sampler = _sampler(unet, True)
+    samples, inter = sampler.sample(S, shape[0], list(shape[1:]), conditioning=(cond[0].cuda(), cond[1], cond[2]),
+                                    unconditional_conditioning=(uncond[0].cuda(), uncond[1], uncond[2]),
+                                    guidance_scale=gs, eta=0.0, x_T=x_T.cuda(), verbose=False, log_every_t=1)
+    assert len(inter["x_inter"]) == len(gold["x_inter"]) == 51
+    ex = [_rel(a, b) for a, b in zip(inter["x_inter"][1:], gold["x_inter"][1:])]
+    ep = [_rel(a, b) for a, b in zip(inter["pred_x0"][1:], gold["pred_x0"][1:])]
+    print(f"ddim {name}: x_inter rel-L2 max {max(ex):.2e} (step {ex.index(max(ex))}), pred_x0 max {max(ep):.2e}, "
+          f"final {_rel(samples, gold['samples']):.3e}")
+    assert max(ex) < DDIM_TOL and _rel(samples, gold["samples"]) < DDIM_TOL
 
 
 def test_ddim_graph_replay_equals_eager(unet):
