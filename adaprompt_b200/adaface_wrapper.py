@@ -58,10 +58,15 @@ class AdaFaceWrapper(nn.Module):
     def load_subj_basis_generator(self, adaface_ckpt_path):
         sbg = self._injected["subj_basis_generator"]
         if sbg is None:
-            # Reference checkpoints are pickled nn.Module objects (embedding_manager.py:1824-1838): unpickling needs the
-            # reference's own classes; convert with `load_state_dict` into adaprompt_b200.subj_basis_generator instead.
-            raise FileNotFoundError(f"no subj_basis_generator injected and {adaface_ckpt_path!r} cannot be unpickled "
-                                    "without the reference package; pass subj_basis_generator=")
+            # Reference checkpoints are pickled nn.Module objects (embedding_manager.py:1824-1838); checkpoint.py unpickles
+            # them without the reference package and converts to the native SubjBasisGenerator (adaface_wrapper.py:50-57).
+            from .checkpoint import load_adaface_ckpt
+            ckpt = load_adaface_ckpt(adaface_ckpt_path, clip_tokenizer=self._injected["tokenizer"])
+            sbgs = ckpt["string_to_subj_basis_generator_dict"]
+            if self.subject_string not in sbgs:
+                raise KeyError(f"Subject '{self.subject_string}' not found in the embedding manager checkpoint "
+                               f"(has {sorted(sbgs)})")
+            sbg = sbgs[self.subject_string]
         self.subj_basis_generator = sbg
         self.subj_basis_generator.num_out_layers = 1                                                 # :59
         self.subj_basis_generator.to(self.device)

