@@ -249,6 +249,7 @@ def test_reference_format_checkpoint_loads_without_the_reference_package():
     # AdaFaceWrapper.load_subj_basis_generator(adaface_ckpt_path) without an injected generator (adaface_wrapper.py:49-59)
     from adaprompt_b200.adaface_wrapper import AdaFaceWrapper
     w = object.__new__(AdaFaceWrapper)
+    torch.nn.Module.__init__(w)
     w.subject_string, w.device, w.is_training = "z", "cpu", False
     w._injected = {"subj_basis_generator": None, "tokenizer": None}
     w.load_subj_basis_generator(os.path.join(gold, "adaface_ckpt_tiny.pt"))
