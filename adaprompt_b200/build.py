@@ -36,7 +36,8 @@ def sources():
 
 def _digest(path: str) -> str:
     h = hashlib.sha1()
-    for dep in [path, os.path.join(CSRC, "common.cuh"), os.path.join(INCLUDE, "adaface_b200.h"), __file__]:
+    headers = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
+    for dep in [path, *headers, os.path.join(INCLUDE, "adaface_b200.h"), __file__]:
         with open(dep, "rb") as f:
             h.update(f.read())
     return h.hexdigest()

@@ -27,6 +27,7 @@
 
 #include "../../include/adaface_b200.h"
 #include "common.cuh"
+#include "attn_tile_common.cuh"
 
 namespace af {
 
@@ -78,46 +79,6 @@ struct TileSmem {
   static_assert(kVAtomBytes % 1024 == 0 && kKBytes % 1024 == 0 && kQBytes % 1024 == 0, "swizzle atoms are 1024-byte aligned");
 };
 
-// lean wait for the hot loops: no printf / globaltimer in the instruction stream, a protocol bug still traps
-__device__ __forceinline__ void mbar_wait_lean(uint32_t addr, uint32_t parity) {
-  if (mbar_try_wait(addr, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(addr, parity)) {
-    if (clock64() - t0 > 8000000000ll) __trap();
-  }
-}
-__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) { mbar_wait_lean(smem_u32(bar), parity); }
-__device__ __forceinline__ void tile_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tile_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-// 2^x on the FMA pipe: round-to-nearest split, degree-3 minimax on [-0.5, 0.5], exponent add (rel. error 1e-4, far
-// below the bf16 rounding of P).  |x| < 2^22; flushes below 2^-126.
-__device__ __forceinline__ float tile_exp2_poly(float x) {
-  x = fmaxf(x, -126.0f);
-  const float t = x + 12582912.0f;             // 1.5 * 2^23: round(x) lands in the low mantissa bits
-  const float f = x - (t - 12582912.0f);       // in [-0.5, 0.5]
-  float pl = fmaf(f, 0.05550410866f, 0.24022650695f);
-  pl = fmaf(pl, f, 0.69314718056f);
-  pl = fmaf(pl, f, 1.0f);
-  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
-}
 template <int POLY>
 __device__ __forceinline__ float tile_exp2(int i, float x) {   // i is a compile-time constant after unrolling
   if constexpr (POLY > 0) {

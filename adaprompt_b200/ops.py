@@ -575,6 +575,26 @@ def quick_gelu(x: torch.Tensor, dy: Optional[torch.Tensor] = None) -> torch.Tens
     return out
 
 
+def attention_bwd(q, k, vp, dop, qT, kT, dOT, lse, delta, *, B, heads, N, d):
+    """dQ [B*N, h*dp], dK [B*N, h*dp], dV [B*N, h*d] (bf16) of the long self-attention (af_attention_bwd_bf16)."""
+    lib = _lib.load()
+    dp = 48 if d == 40 else d
+    dev = q.device
+    dq = torch.empty(B * N, heads * dp, dtype=torch.bfloat16, device=dev)
+    dk = torch.empty(B * N, heads * dp, dtype=torch.bfloat16, device=dev)
+    dv = torch.empty(B * N, heads * d, dtype=torch.bfloat16, device=dev)
+    for t in (q, k, vp, dop, qT, kT, dOT):
+        if t.dtype != torch.bfloat16 or t.stride(-1) != 1:
+            raise ValueError("attention_bwd: bf16 row-major operands expected")
+    rc = lib.af_attention_bwd_bf16(q.data_ptr(), int(q.stride(0)), k.data_ptr(), int(k.stride(0)), vp.data_ptr(),
+                                   int(vp.stride(0)), dop.data_ptr(), int(dop.stride(0)), qT.data_ptr(), int(qT.stride(0)),
+                                   kT.data_ptr(), int(kT.stride(0)), dOT.data_ptr(), int(dOT.stride(0)), lse.data_ptr(),
+                                   delta.data_ptr(), dq.data_ptr(), heads * dp, dk.data_ptr(), heads * dp, dv.data_ptr(),
+                                   heads * d, B, heads, N, d, _stream())
+    _lib.check(rc, "af_attention_bwd_bf16")
+    return dq, dk, dv
+
+
 def rowdot_heads(a: torch.Tensor, b: torch.Tensor, B: int, N: int, heads: int, d: int) -> torch.Tensor:
     lib = _lib.load()
     _chk(a, torch.bfloat16, "a")

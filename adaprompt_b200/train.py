@@ -300,6 +300,23 @@ class AttentionFn(Function):
         ldq, ldk = int(q.stride(0)), int(k.stride(0))
         delta = ops.rowdot_heads(dO, o, B, Nq, h, d)                                  # [B, h, Nq]
         Tq, Tk = B * Nq, B * nkp
+        if d in (40, 80) and Nq == nk == nkp and Nq % 128 == 0 and ops.attention_bwd is not None:
+            # long self-attention: fused tcgen05 backward (attention_bwd.cu), P / dS never leave the SM
+            pad = (lambda t: torch.nn.functional.pad(t.view(-1, h, d), (0, dp - d)).view(-1, h * dp)) if dp != d else (lambda t: t)
+            vp, dop = pad(v), pad(dO)
+            qT = ops.transpose_to_bf16(q[:, :h * dp].contiguous())
+            kT = ops.transpose_to_bf16(k[:, :h * dp].contiguous())
+            dOT = ops.transpose_to_bf16(dop)
+            dq, dk, dv = ops.attention_bwd(q, k, vp, dop, qT, kT, dOT, lse, delta, B=B, heads=h, N=Nq, d=d)
+            if q.shape[1] != h * dp:
+                full = torch.zeros(q.shape, dtype=torch.bfloat16, device=dev)
+                full[:, :h * dp] = dq
+                dq = full
+            if k.shape[1] != h * dp:
+                full = torch.zeros(k.shape, dtype=torch.bfloat16, device=dev)
+                full[:, :h * dp] = dk
+                dk = full
+            return dq, dk, dv, None, None, None, None, None, None
         qT = ops.transpose_to_bf16(q[:, :h * dp].contiguous())                       # [h*dp, Tq_p]
         kT = ops.transpose_to_bf16(k[:, :h * dp].contiguous())                       # [h*dp, Tk_p]
         dOT = ops.transpose_to_bf16(dO)                                              # [C, Tq_p]

@@ -103,6 +103,18 @@ int af_attention_bf16_lse(const void* Q, long long ldq, const void* K, long long
                           int kv_stride, const unsigned char* key_mask, void* O, float* lse, int B, int heads, int Nq,
                           int Nk, int d, af_stream_t stream);
 
+/* Backward of af_attention_bf16_lse for the long self-attention layers (d = 40 / 80, N keys = N queries, N % 128 == 0, no mask):
+ * dQ, dK, dV from dO, the forward operands and the saved lse, with P / dS recomputed tile by tile in tensor memory
+ * (autograd of attention.py:198-242 in the Stage-1 step, ddpm.py:2483-2532).  All matrices bf16 row-major [B*N, ld] with
+ * head h at columns h*DP (DP = 48 zero-padded for d = 40, else d; dV: h*d): Q (pre-scaled, log2 domain), K, Vp = V padded, dOp = dO padded;
+ * QT / KT / dOT = their [heads*48, ld >= B*N] transposes (token contiguous).  lse, delta fp32 [B][heads][N]
+ * (delta_i = sum_c dO_ic O_ic).  dQ / dK [B*N, >= heads*48], dV [B*N, >= heads*40]. */
+int af_attention_bwd_bf16(const void* Q, long long ldq, const void* K, long long ldk, const void* Vp, long long ldv,
+                          const void* dOp, long long lddo, const void* QT, long long ldqt, const void* KT, long long ldkt,
+                          const void* dOT, long long lddot, const float* lse, const float* delta, void* dQ, long long lddq,
+                          void* dK, long long lddk, void* dV, long long lddv, int B, int heads, int N, int d,
+                          af_stream_t stream);
+
 /* af_attention_bf16 on the long-sequence kernel (d in {40, 80}, Nk > 128 and a multiple of 128 / 64, no mask) with an
  * in-kernel clock64 timeline - a measurement aid (scripts/attn_tile_trace.py), results are those of af_attention_bf16.
  * trace: caller-owned device buffer of 512*64*8 + 512 + 2*64*8 int64: [first 512 CTAs (linear id)][key block < 64][8]

@@ -198,8 +198,43 @@ def test_conv_out_dgrad():
 
 
 # ------------------------------------------------------------------------------------------------ attention
+def test_attention_backward_fused_qk_views_match_bgemm_path():
+    """The tcgen05 flash backward (attention_bwd.cu: d = 40, N % 128 == 0) on the layout the UNet uses - q and k are column
+    views of ONE [tokens, Q|K] buffer - against the batched-GEMM backward it replaces (same recomputation from the saved lse,
+    P / dS rounded to bf16 in both): gradients agree to bf16 rounding."""
+    from adaprompt_b200 import ops
+    from adaprompt_b200.train import AttentionFn
+    B, N, d, h, dp = 2, 512, 40, 8, 48
+    sc = d ** -0.5 * math.log2(math.e)
+    qk = torch.zeros(B * N, 2, h, dp, device=DEV)
+    qk[:, 0, :, :d] = _rand(B * N, h, d, seed=11) * sc
+    qk[:, 1, :, :d] = _rand(B * N, h, d, seed=12)
+    qk = qk.reshape(B * N, 2 * h * dp).to(torch.bfloat16)
+    v = _rand(B * N, h * d, seed=13, dtype=torch.bfloat16)
+    dO = _rand(B * N, h * d, seed=14, dtype=torch.bfloat16)
+    grads = []
+    for fused in (True, False):
+        qb = qk[:, :h * dp].detach().requires_grad_(True)
+        kb = qk[:, h * dp:].detach().requires_grad_(True)
+        vb = v.detach().requires_grad_(True)
+        if fused:
+            o = AttentionFn.apply(qb, kb, vb, B, h, d, N, N, N)
+            o.backward(dO)
+        else:
+            orig = ops.attention_bwd
+            ops.attention_bwd = None                  # force the batched-GEMM path
+            try:
+                o = AttentionFn.apply(qb, kb, vb, B, h, d, N, N, N)
+                o.backward(dO)
+            finally:
+                ops.attention_bwd = orig
+        grads.append((qb.grad.clone(), kb.grad.clone(), vb.grad.clone()))
+    for a, b_ in zip(*grads):
+        assert a.shape == b_.shape and _rel(a, b_) < 8e-3
+
+
 @pytest.mark.parametrize("B,N,nk,d", [(2, 256, 256, 40), (1, 1024, 1024, 80), (2, 64, 64, 160), (2, 512, 77, 40), (3, 256, 77, 80),
-                                      (2, 64, 77, 160)])
+                                      (2, 64, 77, 160), (3, 1024, 1024, 40), (1, 4096, 4096, 40), (2, 2304, 2304, 80)])
 def test_attention_backward(B, N, nk, d):
     from adaprompt_b200.packing import head_pad
     from adaprompt_b200.train import AttentionFn
