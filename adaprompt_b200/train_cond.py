@@ -397,6 +397,48 @@ class DistillStep:
         eps = unet_forward_train(self.unet, self.q_sample(x0, t, noise), t, c, dict(self.extra_info))
         return distill_loss(eps, teacher_eps)
 
+    def multi_step_backward(self, batch: Dict[str, torch.Tensor], num_denoising_steps: int, accum: int = 1,
+                            use_graph: bool = False) -> torch.Tensor:
+        """Student multi-step distillation (ddpm.py:2953-3039 with iter_flags['num_denoising_steps'] > 1 and
+        use_arc2face_as_target): the teacher denoises num_denoising_steps times from progressively earlier timesteps
+        (Arc2FaceWrapper.forward :5431-5480); for every step s that fits the accumulation budget
+        (MAX_ACCUMU_BATCH_SIZE = 7: loss_start_step = max(0, ND - 7 // batch), :2967-2968) the student denoises
+        q_sample(pred_x0s[s-1], ts[s], noises[s]) with grad and is matched to the teacher's noise prediction of that step;
+        loss = sum_s MSE_s / sqrt(ND) (:3037).  The reference indexes `arc2face_pred_x0s[s-1]` also for s = 0, i.e. the
+        first student step starts from the teacher's LAST predicted x0 (:2987) - kept, it is what the trainer computes.
+        loss / accum is backpropagated into the trainable parameters' .grad; returns the detached loss."""
+        if self.teacher is None:
+            raise RuntimeError("DistillStep.multi_step_backward needs the Arc2Face teacher")
+        x0, t, noise, face_embs, tokens = batch["x0"], batch["t"], batch["noise"], batch["face_embs"], batch["tokens"]
+        ND = int(num_denoising_steps)
+        with torch.no_grad():
+            prompt_embs, _ = arc2face_forward_face_embs(self.tokenizer, self.arc2face, face_embs, input_max_length=21,
+                                                        return_full_and_core_embs=True)
+            ddpm = _QSampleOnly(self.acp.to(x0.device))
+            preds, pred_x0s, noises, ts = self.teacher(ddpm, x0, noise, t, prompt_embs, num_denoising_steps=ND)
+        loss_start_step = max(0, ND - 7 // x0.shape[0])
+        c = self.context(face_embs, tokens)
+        norm = 1.0 / math.sqrt(ND)
+        total, grad_c = None, None
+        if use_graph:
+            from .train import GraphedUNetLoss
+            g = self.__dict__.setdefault("_graphed", GraphedUNetLoss(self.unet, self.extra_info))
+        for s in range(loss_start_step, ND):
+            x_s = self.q_sample(pred_x0s[s - 1].float(), ts[s], noises[s].float())
+            if use_graph:
+                ls, gs = g(x_s, ts[s], c.detach(), preds[s].float())
+                grad_c = gs if grad_c is None else grad_c + gs
+            else:
+                eps = unet_forward_train(self.unet, x_s, ts[s], c, dict(self.extra_info))
+                ls = distill_loss(eps, preds[s].float())
+            total = ls if total is None else total + ls
+        total = total * norm
+        if use_graph:
+            c.backward(grad_c * (norm / accum))
+            return total
+        (total / accum).backward()
+        return total.detach()
+
     def micro_backward(self, batch: Dict[str, torch.Tensor], accum: int = 1, use_graph: bool = False) -> torch.Tensor:
         """loss / accum backpropagated into the trainable parameters' .grad; returns the detached loss (no host sync).
         use_graph: UNet forward + backward-to-context replayed from one CUDA graph (train.GraphedUNetLoss)."""
