@@ -61,6 +61,9 @@ SIGNATURES = {
     "af_conv3x3_gn_slots": (c_int, [c_int, c_int]),
     "af_gemm_set_pair_mode": (c_int, [c_int]),
     "af_gemm_set_trace": (c_int, [c_void_p]),
+    "af_xattn_explicit": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_void_p, c_void_p,
+                                  c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "af_conv_attn_scores": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "af_attention_bwd_bf16": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong,
                                       c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p,
                                       c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
@@ -159,7 +162,7 @@ KERNELS_PER_CALL = {
     "af_weighted_sum": 1, "af_layernorm_f32": 1,
     "af_conv_in": 1, "af_conv_out": 1, "af_timestep_embedding": 1, "af_linear_small": 1, "af_cast_bf16": 1,
     "af_upsample2x_cast": 1, "af_cfg_ddim_update": 1, "af_advance_step": 1,
-    "af_attention_bf16_lse": 1, "af_attention_bwd_bf16": 2, "af_bgemm_bf16": 1, "af_groupnorm_bwd": 3, "af_layernorm_bwd": 1, "af_geglu_fwd": 1,
+    "af_attention_bf16_lse": 1, "af_attention_bwd_bf16": 2, "af_xattn_explicit": 1, "af_conv_attn_scores": 1, "af_bgemm_bf16": 1, "af_groupnorm_bwd": 3, "af_layernorm_bwd": 1, "af_geglu_fwd": 1,
     "af_geglu_bwd": 1, "af_quick_gelu": 1, "af_rowdot_heads": 1, "af_attention_small_bwd": 1, "af_conv_out_dgrad": 1,
     "af_sumpool2x2": 1, "af_zero_insert2x": 1, "af_transpose_to_bf16": 1, "af_prodigy_moments": 1, "af_prodigy_apply": 1,
     "af_softmax_rows": 1, "af_channel_mix4": 1,

@@ -140,10 +140,13 @@ class ContextKV:
     """Projected cross-attention keys / values of one context: computed once per prompt and reused by
     every DDIM step and both CFG branches (the context is step invariant, ddim.py:243-247)."""
 
-    __slots__ = ("k", "vt", "nk", "nk_pad", "B", "src")
+    __slots__ = ("k", "vt", "nk", "nk_pad", "B", "src", "placeholder2indices")
 
     def __init__(self, k, vt, nk, nk_pad, B, src):
         self.k, self.vt, self.nk, self.nk_pad, self.B, self.src = k, vt, nk, nk_pad, B, src
+        # what the reference's callable context returns next to the tensors (openaimodel.py:920): set by UNetModel.forward
+        # when conv attention is on, read by CrossAttention._run
+        self.placeholder2indices = None
 
 
 class CrossAttention(PackedModule):
@@ -254,24 +257,61 @@ class CrossAttention(PackedModule):
             ops.gemm(x_ln, pk["wq"], q)
             k, vt, ldq, ldk = kv.k, kv.vt, h * dp, h * dp
             nk, kv_stride, ldvt = kv.nk, kv.nk_pad, kv.vt.shape[1]
-        o = torch.empty(T, C, dtype=torch.bfloat16, device=dev)
-        ops.attention(q, k, vt, o, B=B, heads=h, Nq=N, Nk=nk, d=d, ldq=ldq, ldk=ldk, ldvt=ldvt, kv_stride=kv_stride,
-                      key_mask=key_mask)
+        p2i = kv.placeholder2indices if kv is not None else None
+        conv = kv is not None and p2i is not None and self.use_conv_attn_kernel_size is not None \
+            and self.use_conv_attn_kernel_size > 1                      # kernel size 1 leaves the scores alone (ldm/util.py:704)
+        if kv is not None and (self.save_attn_vars or conv):
+            o = self._explicit_cross_attention(q, k, vt, B, N, nk, kv_stride, ldq, ldk, ldvt, p2i if conv else None)
+        else:
+            if self.save_attn_vars:
+                raise NotImplementedError("save_attn_vars on a self-attention layer (the reference only sets it on attn2)")
+            o = torch.empty(T, C, dtype=torch.bfloat16, device=dev)
+            ops.attention(q, k, vt, o, B=B, heads=h, Nq=N, Nk=nk, d=d, ldq=ldq, ldk=ldk, ldvt=ldvt, kv_stride=kv_stride,
+                          key_mask=key_mask)
         ops.gemm(o, pk["wo"], out, bias=pk["bo"], residual=residual)
         return out
 
+    def _explicit_cross_attention(self, q, k, vt, B, N, nk, kv_stride, ldq, ldk, ldvt, placeholder2indices):
+        """The score-materialising path (xattn_explicit.cu) for save_attn_vars (attention.py:245-255) and conv attention
+        (:208-216 -> ldm/util.py:700-878).  Returns o bf16 [B*N, C]; fills self.cached_activations when saving."""
+        h, d = self.heads, self.dim_head
+        dev = q.device
+        common = dict(B=B, heads=h, N=N, nk=nk, d=d, ldq=ldq, ldk=ldk, ldvt=ldvt, kv_stride=kv_stride)
+        override = cols = None
+        if placeholder2indices is not None:
+            ks = int(self.use_conv_attn_kernel_size)
+            if self.infeat_size is None or self.infeat_size[0] * self.infeat_size[1] != N:
+                raise ValueError("conv attention needs infeat_size = the (H, W) of the query map (set by SpatialTransformer)")
+            Hf, Wf = self.infeat_size
+            point = ops.xattn_explicit(q, k, vt, want_out=False, want_scores=True, **common)["attnscore"]
+            ovs, cls = [], []
+            for subj_string in placeholder2indices:                        # :209-216, one replacement per subject string
+                indices_B, indices_N = placeholder2indices[subj_string]
+                uniq = torch.unique(indices_B)
+                BS = len(uniq)
+                M = len(indices_N) // BS
+                if ks * ks > M:
+                    raise ValueError(f"{M} embeddings are not enough to cover a {ks}x{ks} kernel.")
+                c = torch.full((B, ks * ks), -1, dtype=torch.int32, device=dev)
+                c[uniq.to(dev).long()] = indices_N.reshape(BS, M)[:, :ks * ks].to(device=dev, dtype=torch.int32)
+                ovs.append(ops.conv_attn_scores(point, c, B=B, heads=h, Hf=Hf, Wf=Wf, nk=nk, ks=ks))
+                cls.append(c)
+            override, cols = torch.cat(ovs, dim=-1).contiguous(), torch.cat(cls, dim=-1).contiguous()
+        save = self.save_attn_vars
+        r = ops.xattn_explicit(q, k, vt, override=override, ov_cols=cols, want_out=True, want_scores=save, want_attn=save,
+                               want_q=save, **common)
+        if save:
+            self.cached_activations = {"q": r["q"], "attn": r["attn"], "attnscore": r["attnscore"]}
+        return r["out"]
+
     def forward(self, x, context=None, mask=None):
         """Reference signature (attention.py:172): x [B,N,C]; context None | tensor | (v_ctx, k_ctx) | callable."""
-        if self.save_attn_vars:
-            raise NotImplementedError("save_attn_vars (training-time attention capture) is not implemented")
         B, N, C = x.shape
         context_provided = exists(context)
         if callable(context):
             context, placeholder2indices = context()
         else:
             placeholder2indices = None
-        if context_provided and placeholder2indices is not None and self.use_conv_attn_kernel_size > 0:
-            raise NotImplementedError("conv attention (use_conv_attn_kernel_size > 0) is not implemented")
         kv = None
         if context_provided:
             if isinstance(context, (list, tuple)):
@@ -279,6 +319,7 @@ class CrossAttention(PackedModule):
             else:
                 v_context = k_context = context
             kv = self.project_context(k_context, v_context)
+            kv.placeholder2indices = placeholder2indices
         km = None
         if exists(mask):
             km = mask.reshape(B, -1).bool().to(torch.uint8).contiguous()

@@ -130,7 +130,8 @@ class DDIMSampler(object):
 
         plain = (mask is None and callback is None and img_callback is None and score_corrector is None
                  and not quantize_denoised and noise_dropout == 0. and not ddim_use_original_steps
-                 and isinstance(cond, tuple) and img.is_cuda)
+                 and isinstance(cond, tuple) and img.is_cuda
+                 and not (cond[2] or {}).get("capture_distill_attn", False))     # captured activations are per-call tensors
         if plain and self.use_cuda_graph:
             scales = []
             g = guide_scale

@@ -575,6 +575,31 @@ def quick_gelu(x: torch.Tensor, dy: Optional[torch.Tensor] = None) -> torch.Tens
     return out
 
 
+def xattn_explicit(q, k, vt, *, B, heads, N, nk, d, ldq, ldk, ldvt, kv_stride, override=None, ov_cols=None,
+                   want_out=True, want_scores=False, want_attn=False, want_q=False):
+    """Materialised-score cross-attention (af_xattn_explicit).  -> dict(out, attnscore, attn, q) of the requested parts."""
+    lib = _lib.load()
+    dev = q.device
+    r = {"out": torch.empty(B * N, heads * d, dtype=torch.bfloat16, device=dev) if want_out else None,
+         "attnscore": torch.empty(B, heads, N, nk, dtype=torch.float32, device=dev) if want_scores else None,
+         "attn": torch.empty(B, heads, N, nk, dtype=torch.float32, device=dev) if want_attn else None,
+         "q": torch.empty(B, heads, N, d, dtype=torch.float32, device=dev) if want_q else None}
+    n_ov = int(ov_cols.shape[1]) if ov_cols is not None else 0
+    rc = lib.af_xattn_explicit(q.data_ptr(), ldq, k.data_ptr(), ldk, vt.data_ptr(), ldvt, kv_stride, _p(override),
+                               _p(ov_cols), n_ov, _p(r["out"]), _p(r["attn"]), _p(r["attnscore"]), _p(r["q"]), B, heads, N,
+                               nk, d, _stream())
+    _lib.check(rc, "af_xattn_explicit")
+    return r
+
+
+def conv_attn_scores(score, cols, *, B, heads, Hf, Wf, nk, ks):
+    lib = _lib.load()
+    ov = torch.empty(B, heads, Hf * Wf, ks * ks, dtype=torch.float32, device=score.device)
+    rc = lib.af_conv_attn_scores(score.data_ptr(), cols.data_ptr(), B, heads, Hf, Wf, nk, ks, ov.data_ptr(), _stream())
+    _lib.check(rc, "af_conv_attn_scores")
+    return ov
+
+
 def attention_bwd(q, k, vp, dop, qT, kT, dOT, lse, delta, *, B, heads, N, d):
     """dQ [B*N, h*dp], dK [B*N, h*dp], dV [B*N, h*d] (bf16) of the long self-attention (af_attention_bwd_bf16)."""
     lib = _lib.load()

@@ -434,6 +434,9 @@ def unet_forward_train(unet: UNetModel, x: torch.Tensor, timesteps: torch.Tensor
         raise ValueError("extra_info['use_layerwise_context'] must be True")
     if extra_info.get("img_mask", None) is not None or extra_info.get("capture_distill_attn", False):
         raise NotImplementedError("training step: img_mask / capture_distill_attn")
+    if extra_info.get("use_conv_attn_kernel_size", -1) > 0 and extra_info.get("placeholder2indices", None) is not None:
+        raise NotImplementedError("training step: the backward of conv attention is not built (zero-shot distillation runs "
+                                  "with use_conv_attn_kernel_size = -1)")
     iter_type = extra_info.get("iter_type", "normal_recon")
     pk = unet.packed()
     B = x.shape[0]

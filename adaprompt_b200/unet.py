@@ -576,8 +576,8 @@ class UNetModel(PackedModule):
             # the reference's non-layerwise branch returns a 3-tuple that CrossAttention cannot unpack
             # (openaimodel.py:872 vs attention.py:186): only the layerwise path is live.
             raise ValueError("extra_info['use_layerwise_context'] must be True")
-        if capture_distill_attn or debug_attn:
-            raise NotImplementedError("capture_distill_attn / debug_attn (training-time attention capture)")
+        if debug_attn:
+            raise NotImplementedError("debug_attn (the reference drops into breakpoint(), openaimodel.py:1037-1038)")
         B = x.shape[0]
         if apply_compel_cfg_prob > 0:
             kvs = self.compel_context_kv(context, B, iter_type, ei.get("empty_context", None), apply_compel_cfg_prob,
@@ -592,18 +592,28 @@ class UNetModel(PackedModule):
         old_ca_flags, _ = self.set_cross_attn_flags(
             ca_flag_dict={"use_conv_attn_kernel_size:layerwise": sizes, "is_training": is_training},
             ca_layer_indices=None)
-        if use_conv_attn_kernel_size > 0 and placeholder2indices is not None:
-            self.set_cross_attn_flags(ca_flag_dict=old_ca_flags, ca_layer_indices=None)
-            raise NotImplementedError("conv attention (use_conv_attn_kernel_size > 0) is not implemented")
+        conv_on = use_conv_attn_kernel_size > 0 and placeholder2indices is not None
+        for kv in kvs.values():                         # what get_layer_context returns next to the tensors (:920)
+            kv.placeholder2indices = placeholder2indices if conv_on else None
+        distill_layer_indices, distill_old = [], None
+        if capture_distill_attn:                                                          # :947-952
+            distill_layer_indices = [7, 8, 12, 16, 17, 18, 19, 20, 21, 22, 23, 24]
+            distill_old, _ = self.set_cross_attn_flags(ca_flag_dict={"save_attn_vars": True},
+                                                       ca_layer_indices=distill_layer_indices)
+        acts = {}
         try:
-            out = self._forward_nhwc(x, timesteps, kvs, img_mask)
+            out = self._forward_nhwc(x, timesteps, kvs, img_mask, distill_layer_indices, acts)
         finally:
+            if distill_old is not None:
+                self.set_cross_attn_flags(ca_flag_dict=distill_old, ca_layer_indices=distill_layer_indices)
             self.set_cross_attn_flags(ca_flag_dict=old_ca_flags, ca_layer_indices=None)
-        empty = {key: {} for key in ("outfeat", "attn", "attnscore", "q")}
-        extra_info["ca_layers_activations"] = empty                                       # :1031-1035
+            for kv in kvs.values():
+                kv.placeholder2indices = None
+        extra_info["ca_layers_activations"] = {key: {li: acts[li][key] for li in acts}
+                                               for key in ("outfeat", "attn", "attnscore", "q")}      # :1031-1035
         return out
 
-    def _forward_nhwc(self, x, timesteps, kvs, img_mask):
+    def _forward_nhwc(self, x, timesteps, kvs, img_mask, capture_layers=(), acts=None):
         pk = self.packed()
         _, rows = self.time_embedding(timesteps)
         offs = pk["emb_offs"]
@@ -615,14 +625,24 @@ class UNetModel(PackedModule):
         hs = []
         h = Act(x)
         layer_idx = 0
+        def capture(module, h, layer_idx):                                                # :984-988, 996-1000, 1023-1027
+            if layer_idx in capture_layers:
+                attn2 = module[1].transformer_blocks[0].attn2
+                acts[layer_idx] = dict(attn2.cached_activations)
+                acts[layer_idx]["outfeat"] = h.t.permute(0, 3, 1, 2)       # NCHW view of the NHWC residual stream
+                attn2.cached_activations = None
+
         for module in self.input_blocks:                                                   # :977-990
             h = module._run((h,), emb_rows_of, kvs.get(layer_idx), img_mask)
             hs.append(h)
+            capture(module, h, layer_idx)
             layer_idx += 1
         h = self.middle_block._run((h,), emb_rows_of, kvs.get(layer_idx), img_mask)        # :995
+        capture(self.middle_block, h, layer_idx)
         layer_idx += 1
         for module in self.output_blocks:                                                  # :1016-1029
             h = module._run((h, hs.pop()), emb_rows_of, kvs.get(layer_idx), img_mask)
+            capture(module, h, layer_idx)
             layer_idx += 1
         B, H, W, C = h.t.shape
         dev = h.t.device

@@ -103,6 +103,23 @@ int af_attention_bf16_lse(const void* Q, long long ldq, const void* K, long long
                           int kv_stride, const unsigned char* key_mask, void* O, float* lse, int B, int heads, int Nq,
                           int Nk, int d, af_stream_t stream);
 
+/* Cross-attention over <= 96 prompt tokens with the score matrix materialised (operands as af_attention_bf16): the two
+ * optional behaviours of CrossAttention.forward that need the scores themselves - save_attn_vars (attention.py:245-255:
+ * q_out = q * sqrt(scale) [B][heads][N][d], attnscore = sim after replacement, attn = softmax; any of them may be NULL)
+ * and conv attention (attention.py:208-216): override_scores [B][heads][N][n_ov] replace the score columns ov_cols
+ * [B][n_ov] (int32, -1 = keep) before the softmax.  O [B*N, heads*d] bf16 or NULL.  Scores are in the reference's domain
+ * (q.k * d^-1/2). */
+int af_xattn_explicit(const void* Q, long long ldq, const void* K, long long ldk, const void* Vt, long long ldvt,
+                      int kv_stride, const float* override_scores, const int* ov_cols, int n_ov, void* O, float* attn,
+                      float* attnscore, float* q_out, int B, int heads, int N, int nk, int d, af_stream_t stream);
+/* replace_rows_by_conv_attn (ldm/util.py:700-878) from POINTWISE scores: score fp32 [B][heads][Hf*Wf][nk] (attnscore of
+ * af_xattn_explicit), cols int32 [B][ks*ks] = the prompt positions of the first ks*ks subject tokens of each sample
+ * (cols[b][0] < 0: sample without the subject -> zeros).  override_scores [B][heads][Hf*Wf][ks*ks]: column m is the
+ * ks x ks grouped convolution of the query map with those tokens' keys, divided by ks^1.5 and shifted by token m's
+ * offset (dy, dx), zero outside the map. */
+int af_conv_attn_scores(const float* score, const int* cols, int B, int heads, int Hf, int Wf, int nk, int ks,
+                        float* override_scores, af_stream_t stream);
+
 /* Backward of af_attention_bf16_lse for the long self-attention layers (d = 40 / 80, N keys = N queries, N % 128 == 0, no mask):
  * dQ, dK, dV from dO, the forward operands and the saved lse, with P / dS recomputed tile by tile in tensor memory
  * (autograd of attention.py:198-242 in the Stage-1 step, ddpm.py:2483-2532).  All matrices bf16 row-major [B*N, ld] with

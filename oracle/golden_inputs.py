@@ -55,6 +55,15 @@ def unet_inputs(name: str):
                      empty_context=torch.randn(1, 77, 768, generator=g), python_random_seed=1234)
         return torch.randn(2, 4, 32, 32, generator=g), torch.tensor([341, 341]), \
             torch.randn(32, 77, 768, generator=g), extra
+    if name == "b2_t601_convattn_capture_32":
+        # conv attention (use_conv_attn_kernel_size 3: attention.py:208-216, ldm/util.py:700-878) on sample 0 only (its
+        # prompt holds the 16 subject tokens at positions 5..20; sample 1 has none) + attention / feature capture
+        # (capture_distill_attn: openaimodel.py:947-952,984-988,1031-1035)
+        g = _g(14)
+        extra.update(use_conv_attn_kernel_size=3, capture_distill_attn=True,
+                     placeholder2indices={"z": (torch.zeros(16, dtype=torch.long), torch.arange(5, 21))})
+        return torch.randn(2, 4, 32, 32, generator=g), torch.tensor([601, 601]), \
+            torch.randn(32, 77, 768, generator=g), extra
     raise KeyError(name)
 
 

@@ -62,6 +62,22 @@ def main():
     if cases2:
         torch.save(cases2, os.path.join(OUT, "unet_eps_r02.pt"))
 
+    # ---- 1c. conv attention + attention capture (own file) -------------------------------------------------
+    if only and "capture" in only:
+        name = "b2_t601_convattn_capture_32"
+        x, t, ctx, extra = unet_inputs(name)
+        with torch.no_grad():
+            eps = unet(x, t, context=ctx, extra_info=extra)
+        acts = extra["ca_layers_activations"]
+        keep = {}
+        for li in (7, 12, 20):      # 8x8, 4x4 and 16x16 feature maps; fp16 keeps the fixture small
+            keep[li] = {k: acts[k][li].detach().to(torch.float16).clone() for k in ("outfeat", "attn", "attnscore", "q")}
+        torch.save({name: {"eps": eps.clone(), "acts": keep, "layers": sorted(acts["attn"].keys()), "x_sum": checksum(x),
+                           "ctx_sum": checksum(ctx)}}, os.path.join(OUT, "unet_capture_r02.pt"))
+        print(f"capture: layers {sorted(acts['attn'].keys())}, |eps|={eps.abs().mean():.4f}, "
+              f"attn[20] {tuple(acts['attn'][20].shape)} q[20] {tuple(acts['q'][20].shape)} outfeat[20] {tuple(acts['outfeat'][20].shape)}")
+        return
+
     # ---- 2. module-level ---------------------------------------------------------------------------
     mods = {}
     mi = module_inputs()

@@ -172,9 +172,35 @@ def res_block(sd: SD, p: str, x: torch.Tensor, emb: torch.Tensor) -> torch.Tenso
     return x + h
 
 
-def cross_attention(sd: SD, p: str, x: torch.Tensor, context=None, mask=None, heads: int = 8) -> torch.Tensor:
+def conv_attn_columns(sim_point: torch.Tensor, cols: torch.Tensor, infeat_size, ks: int) -> torch.Tensor:
+    """replace_rows_by_conv_attn (ldm/util.py:700-878) for ONE sample, restated on pointwise scores: the grouped conv2d
+    of the zero-padded query map with the ks*ks subject keys as kernel taps (:797-809) is the sum over taps (i, j) of the
+    pointwise score map of tap key ks*i+j read at pixel offset (i - pad, j - pad); token m = (dy + pad) * ks + (dx + pad)
+    receives that map shifted by (dy, dx) with zeros shifted in (:811-845), all divided by ks^1.5 (:766,:803).
+    sim_point [H, N, T] (scaled scores of this sample), cols [ks*ks] token positions -> [ks*ks, H, N]."""
+    Hf, Wf = infeat_size
+    Hh = sim_point.shape[0]
+    pad = (ks - 1) // 2
+    g = sim_point[:, :, cols].reshape(Hh, Hf, Wf, ks * ks)
+    gp = F.pad(g.permute(0, 3, 1, 2), (ks, ks, ks, ks))                      # [H, taps, Hf + 2ks, Wf + 2ks]
+    A = torch.zeros(Hh, Hf, Wf, dtype=sim_point.dtype)
+    for i in range(ks):
+        for j in range(ks):
+            A = A + gp[:, ks * i + j, ks + i - pad: ks + i - pad + Hf, ks + j - pad: ks + j - pad + Wf]
+    A = A / ks ** 1.5
+    Ap = F.pad(A, (ks, ks, ks, ks))
+    out = []
+    for m in range(ks * ks):
+        dy, dx = m // ks - pad, m % ks - pad
+        out.append(Ap[:, ks - dy: ks - dy + Hf, ks - dx: ks - dx + Wf].reshape(Hh, Hf * Wf))
+    return torch.stack(out, 0)
+
+
+def cross_attention(sd: SD, p: str, x: torch.Tensor, context=None, mask=None, heads: int = 8, conv_attn=None,
+                    capture: Optional[dict] = None) -> torch.Tensor:
     """CrossAttention.forward (attention.py:172-243); context None -> self-attention; context may be a
-    (v_context, k_context) tuple (:190-193); mask is a key mask [B, ...] (:223-232)."""
+    (v_context, k_context) tuple (:190-193); mask is a key mask [B, ...] (:223-232).  conv_attn = (placeholder2indices,
+    infeat_size, ks) replaces score columns (:208-216); capture: dict filled with q / attn / attnscore (:245-255)."""
     B, N, C = x.shape
     q = F.linear(x, sd[p + ".to_q.weight"])
     if context is None:
@@ -192,10 +218,24 @@ def cross_attention(sd: SD, p: str, x: torch.Tensor, context=None, mask=None, he
 
     q, k, v = split(q), split(k), split(v)
     sim = torch.einsum("bhid,bhjd->bhij", q, k) * (d ** -0.5)
+    if conv_attn is not None and context is not None:
+        p2i, infeat_size, ks = conv_attn
+        if p2i is not None and ks > 1:
+            sim2 = sim.clone()
+            for subj in p2i:
+                iB, iN = p2i[subj]
+                uniq = torch.unique(iB)
+                M = len(iN) // len(uniq)
+                for bi, b_ in enumerate(uniq.tolist()):
+                    cols = iN[bi * M: bi * M + ks * ks]
+                    sim2[b_][:, :, cols] = conv_attn_columns(sim[b_], cols, infeat_size, ks).permute(1, 2, 0)
+            sim = sim2
     if mask is not None:
         m = mask.reshape(B, -1).bool()
         sim = sim.masked_fill(~m[:, None, None, :], -torch.finfo(sim.dtype).max)
     attn = sim.softmax(dim=-1)
+    if capture is not None:
+        capture.update(q=q * (d ** -0.5) ** 0.5, attn=attn, attnscore=sim)
     out = torch.einsum("bhij,bhjd->bhid", attn, v).permute(0, 2, 1, 3).reshape(B, N, C)
     return F.linear(out, sd[p + ".to_out.0.weight"], sd[p + ".to_out.0.bias"])
 
@@ -207,25 +247,27 @@ def feed_forward(sd: SD, p: str, x: torch.Tensor) -> torch.Tensor:
     return F.linear(val * F.gelu(gate), sd[p + ".net.2.weight"], sd[p + ".net.2.bias"])
 
 
-def basic_transformer_block(sd: SD, p: str, x, context=None, mask=None, heads: int = 8):
+def basic_transformer_block(sd: SD, p: str, x, context=None, mask=None, heads: int = 8, conv_attn=None, capture=None):
     """BasicTransformerBlock._forward (attention.py:275-285): the mask goes to self-attention only."""
     def ln(t, n):
         return F.layer_norm(t, (t.shape[-1],), sd[f"{p}.{n}.weight"], sd[f"{p}.{n}.bias"], 1e-5)
 
     x1 = cross_attention(sd, p + ".attn1", ln(x, "norm1"), None, mask, heads) + x
-    x2 = x1 + cross_attention(sd, p + ".attn2", ln(x1, "norm2"), context, None, heads)
+    x2 = x1 + cross_attention(sd, p + ".attn2", ln(x1, "norm2"), context, None, heads, conv_attn, capture)
     return feed_forward(sd, p + ".ff", ln(x2, "norm3")) + x2
 
 
-def spatial_transformer(sd: SD, p: str, x: torch.Tensor, context=None, mask=None, heads: int = 8):
-    """SpatialTransformer.forward (attention.py:321-341): GroupNorm eps 1e-6, 1x1 convs, depth 1."""
+def spatial_transformer(sd: SD, p: str, x: torch.Tensor, context=None, mask=None, heads: int = 8, conv=None, capture=None):
+    """SpatialTransformer.forward (attention.py:321-341): GroupNorm eps 1e-6, 1x1 convs, depth 1.  conv = (placeholder2indices,
+    kernel size) of this layer's conv attention or None; capture: dict for the attn2 activations."""
     B, C, H, W = x.shape
     x_in = x
     h = F.group_norm(x, 32, sd[p + ".norm.weight"], sd[p + ".norm.bias"], 1e-6)
     h = F.conv2d(h, sd[p + ".proj_in.weight"], sd[p + ".proj_in.bias"])
     h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)
     m2 = F.interpolate(mask, size=(H, W), mode="nearest") if mask is not None else None
-    h = basic_transformer_block(sd, p + ".transformer_blocks.0", h, context, m2, heads)
+    conv_attn = (conv[0], (H, W), conv[1]) if conv is not None else None           # infeat_size (:330)
+    h = basic_transformer_block(sd, p + ".transformer_blocks.0", h, context, m2, heads, conv_attn, capture)
     h = h.reshape(B, H, W, C).permute(0, 3, 1, 2)
     return F.conv2d(h, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"]) + x_in
 
@@ -241,6 +283,13 @@ def unet_forward(sd: SD, spec: UNetSpec, x: torch.Tensor, timesteps: torch.Tenso
     emb = F.linear(F.silu(emb), sd["time_embed.2.weight"], sd["time_embed.2.bias"])
     ctx = context.reshape(B, 16, -1, context.shape[-1]).permute(1, 0, 2, 3)  # :866
 
+    conv_ks = extra_info.get("use_conv_attn_kernel_size", -1) or -1
+    p2i = extra_info.get("placeholder2indices", None)
+    conv_sizes = [conv_ks] * 16
+    if conv_ks > 0:
+        conv_sizes[6:11] = [1] * 5                                               # openaimodel.py:932
+    distill_layers = [7, 8, 12, 16, 17, 18, 19, 20, 21, 22, 23, 24] if extra_info.get("capture_distill_attn", False) else []
+    acts: Dict[int, dict] = {}
     compel_prob = extra_info.get("apply_compel_cfg_prob", 0)
     empty_ctx, compel_range = extra_info.get("empty_context", None), extra_info.get("compel_cfg_weight_level_range", None)
     is_training = extra_info.get("is_training", True)
@@ -281,7 +330,12 @@ def unet_forward(sd: SD, spec: UNetSpec, x: torch.Tensor, timesteps: torch.Tenso
             elif l[0] == "res":
                 h = res_block(sd, p, h, emb)
             elif l[0] == "attn":
-                h = spatial_transformer(sd, p, h, layer_ctx(layer_idx), mask, spec.num_heads)
+                cap = {} if layer_idx in distill_layers else None
+                ks = conv_sizes[LAYER2CA[layer_idx]]
+                h = spatial_transformer(sd, p, h, layer_ctx(layer_idx), mask, spec.num_heads,
+                                        (p2i, ks) if (conv_ks > 0 and p2i is not None) else None, cap)
+                if cap is not None:
+                    acts[layer_idx] = cap
             elif l[0] == "down":
                 h = F.conv2d(h, sd[p + ".op.weight"], sd[p + ".op.bias"], stride=2, padding=1)
             elif l[0] == "up":
@@ -293,16 +347,25 @@ def unet_forward(sd: SD, spec: UNetSpec, x: torch.Tensor, timesteps: torch.Tenso
     hs = []
     h = x.float()
     layer_idx = 0
+    def outfeat(h, layer_idx):                     # openaimodel.py:984-988: the block output next to the attn2 activations
+        if layer_idx in acts:
+            acts[layer_idx]["outfeat"] = h
+
     for i, layers in enumerate(inp):
         h = run(f"input_blocks.{i}", layers, h, layer_idx)
         hs.append(h)
+        outfeat(h, layer_idx)
         layer_idx += 1
     h = run("middle_block", mid, h, layer_idx)
+    outfeat(h, layer_idx)
     layer_idx += 1
     for i, layers in enumerate(out):
         h = torch.cat([h, hs.pop()], dim=1)  # :1019
         h = run(f"output_blocks.{i}", layers, h, layer_idx)
+        outfeat(h, layer_idx)
         layer_idx += 1
+    if extra_info is not None and distill_layers:  # :1031-1035
+        extra_info["ca_layers_activations"] = {k: {li: acts[li][k] for li in acts} for k in ("outfeat", "attn", "attnscore", "q")}
     h = F.silu(group_norm32(h, sd["out.0.weight"], sd["out.0.bias"]))
     return F.conv2d(h, sd["out.2.weight"], sd["out.2.bias"], padding=1)
 

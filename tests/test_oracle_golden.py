@@ -81,6 +81,27 @@ def test_ddim_oracle_matches_reference_every_step_g10_4(sd):
             assert _rel(pred, gold["pred_x0"][i + 1]) < 1e-4, i
 
 
+def test_unet_oracle_conv_attention_and_capture_match_reference(sd):
+    """use_conv_attn_kernel_size = 3 with subject tokens on sample 0 (attention.py:208-216, ldm/util.py:700-878) and
+    capture_distill_attn (openaimodel.py:947-952,984-988,1031-1035): eps and the captured q / attn / attnscore / outfeat
+    of layers 7, 12, 20 against the unmodified reference (fixture stored in fp16)."""
+    from oracle.golden_inputs import checksum, unet_inputs
+    from oracle.unet_oracle import UNetSpec, unet_forward
+    name = "b2_t601_convattn_capture_32"
+    gold = torch.load(os.path.join(GOLD, "unet_capture_r02.pt"))[name]
+    x, t, ctx, extra = unet_inputs(name)
+    assert abs(checksum(x) - gold["x_sum"]) < 1e-6 * gold["x_sum"]
+    with torch.no_grad():
+        eps = unet_forward(sd, UNetSpec(), x, t, ctx, extra)
+    assert _rel(eps, gold["eps"]) < 1e-5
+    acts = extra["ca_layers_activations"]
+    assert sorted(acts["attn"].keys()) == gold["layers"]
+    for li, g in gold["acts"].items():
+        for k in ("outfeat", "attn", "attnscore", "q"):
+            assert acts[k][li].shape == g[k].shape, (li, k)
+            assert _rel(acts[k][li], g[k].float()) < 2e-3, (li, k)          # fp16 fixture
+
+
 def test_module_oracles_match_reference(sd):
     from oracle import unet_oracle as uo
     from oracle.golden_inputs import module_inputs

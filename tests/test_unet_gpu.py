@@ -82,6 +82,38 @@ def test_unet_eps_vs_reference_golden_round2(unet, name):
     assert max(errs) < EPS_TOL
 
 
+def test_unet_conv_attention_and_capture_vs_reference_golden(unet):
+    """Conv attention (kernel 3, subject tokens on sample 0 only) + capture_distill_attn through the score-materialising
+    cross-attention path (xattn_explicit.cu), against the unmodified reference: eps, and q / attn / attnscore / outfeat
+    of layers 7 (8x8), 12 (4x4) and 20 (16x16)."""
+    from oracle.golden_inputs import unet_inputs
+    name = "b2_t601_convattn_capture_32"
+    gold = torch.load(os.path.join(GOLD, "unet_capture_r02.pt"))[name]
+    x, t, ctx, extra = unet_inputs(name)
+    extra = _cuda_extra(extra)
+    with torch.no_grad():
+        eps = unet(x.cuda(), t.cuda(), context=ctx.cuda(), extra_info=extra)
+    err = _rel(eps, gold["eps"])
+    acts = extra["ca_layers_activations"]
+    assert sorted(acts["attn"].keys()) == gold["layers"]
+    errs = {}
+    for li, g in gold["acts"].items():
+        for k in ("outfeat", "attn", "attnscore", "q"):
+            assert tuple(acts[k][li].shape) == tuple(g[k].shape), (li, k, acts[k][li].shape, g[k].shape)
+            errs[(li, k)] = _rel(acts[k][li], g[k].float())
+    print(f"conv-attn + capture: eps rel-L2 {err:.3e}; activations {({k: '%.1e' % v for k, v in errs.items()})}")
+    assert err < EPS_TOL
+    assert max(errs.values()) < 2e-2
+    # with the same inputs but no subject indices the conv path is off and the scores differ (the replacement is live)
+    x2, t2, ctx2, extra2 = unet_inputs(name)
+    extra2["placeholder2indices"] = None
+    extra2 = _cuda_extra(extra2)
+    with torch.no_grad():
+        unet(x2.cuda(), t2.cuda(), context=ctx2.cuda(), extra_info=extra2)
+    a, b_ = acts["attnscore"][20][0, :, :, 5:14], extra2["ca_layers_activations"]["attnscore"][20][0, :, :, 5:14]
+    assert _rel(a, b_) > 0.1
+
+
 def test_unet_batch16_pair_mode_on_off_bit_identical(unet):
     """cta_group::2 pair tiles (auto-enabled at batch 16) vs single-CTA tiles over the WHOLE UNet: same accumulation
     order, so the eps must be bit-identical."""
