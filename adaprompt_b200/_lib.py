@@ -32,6 +32,8 @@ class AfEpilogue(Structure):
         ("geglu", c_int),
         ("act", c_int),
         ("gn_stats", c_void_p),
+        ("pair_mode", c_int),
+        ("trace", c_void_p),
     ]
 
 
@@ -59,8 +61,6 @@ SIGNATURES = {
     "af_attention_bf16": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_void_p,
                                   c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "af_conv3x3_gn_slots": (c_int, [c_int, c_int]),
-    "af_gemm_set_pair_mode": (c_int, [c_int]),
-    "af_gemm_set_trace": (c_int, [c_void_p]),
     "af_xattn_explicit": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_void_p, c_void_p,
                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "af_conv_attn_scores": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

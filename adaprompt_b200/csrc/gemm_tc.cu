@@ -57,7 +57,7 @@ struct GemmParams {
   void* out;
   long long ldo;
   int out_bf16;
-  long long* trace;        // optional timeline of CTA 0: [3 actors][32 tiles][8 events] clock64 (af_gemm_set_trace)
+  long long* trace;        // optional timeline of CTA 0: [3 actors][32 tiles][8 events] clock64 (af_epilogue.trace)
   int geglu;               // tile cols [0,BN/2) = value, [BN/2,BN) = gate; writes BN/2 cols
   int act;                 // 0 none, 1 quick_gelu x*sigmoid(1.702x) on (acc + bias), before the residual add
   float* gn_stats;         // [slots_total][N][2] per-channel (sum, sumsq) over 32-row quarters of the output, or null
@@ -602,8 +602,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static long long* g_gemm_trace = nullptr;
-static int g_pair_mode = 1;   // 1: CTA pairs (cta_group::2) whenever a GEMM has at least two 128-row tiles; 0: never
+// No process-global switches: the tile schedule (af_epilogue.pair_mode) and the timeline probe (af_epilogue.trace) are
+// per-call options.
 
 template <int BN, bool GEGLU, int SLOTS, bool CTA2>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
@@ -643,9 +643,9 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
 // Measured on B200 (profiles/r01_pair_vs_single.md): the pair schedule wins for linear GEMMs with N tiles >= 160 and
 // at least two waves of pair tiles (+7 % on the FF2 shapes, +17 % on 8192^3 with 256-wide tiles) and loses ~3 % on the
 // implicit-GEMM convolutions, so mode 1 ("auto") uses it only there; mode 2 forces it wherever it is legal (tests).
-static bool want_pair(int m_tiles, int n_tiles, int bn, int amode) {
-  if (g_pair_mode == 0 || m_tiles < 2) return false;
-  if (g_pair_mode == 2) return true;
+static bool want_pair(int pair_mode, int m_tiles, int n_tiles, int bn, int amode) {
+  if (pair_mode == AF_PAIR_NEVER || m_tiles < 2) return false;
+  if (pair_mode == AF_PAIR_ALWAYS) return true;
   return amode == 0 && bn >= 160 && ((m_tiles + 1) / 2) * n_tiles >= num_sms();
 }
 
@@ -747,17 +747,6 @@ static int fill_epilogue(GemmParams& p, const af_epilogue* ep, long long default
 
 using namespace af;
 
-extern "C" int af_gemm_set_trace(long long* device_buffer) {
-  af::g_gemm_trace = device_buffer;
-  return 0;
-}
-
-extern "C" int af_gemm_set_pair_mode(int mode) {
-  const int old = g_pair_mode;
-  g_pair_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
-  return old;
-}
-
 extern "C" int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* A1, long long lda1, int K1,
                             const void* Wt, int M, int N, const af_epilogue* ep, int bn_hint, cudaStream_t stream) {
   AF_CHECK_ARG(A0 && Wt && ep, "af_gemm_bf16: null pointer");
@@ -768,10 +757,10 @@ extern "C" int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* 
                "af_gemm_bf16: K / lda must be multiples of 8 (16-byte TMA strides)");
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.trace = g_gemm_trace;
+  p.trace = ep->trace;
   const int K = K0 + K1;
   const int bn = pick_bn(N, ep->geglu, bn_hint);
-  const bool pair = want_pair((M + 127) / 128, (N + bn - 1) / bn, bn, 0);
+  const bool pair = want_pair(ep->pair_mode, (M + 127) / 128, (N + bn - 1) / bn, bn, 0);
   AF_CHECK_ARG(!ep->geglu || N % 256 == 0, "geglu: packed N=%d must be a multiple of 256", N);
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K0), static_cast<uint64_t>(M)};
@@ -839,13 +828,13 @@ extern "C" int af_conv3x3_bf16(const void* X0, int C0, const void* X1, int C1, c
   AF_CHECK_ARG(!ep->geglu, "af_conv3x3_bf16: geglu epilogue unsupported");
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.trace = g_gemm_trace;
+  p.trace = ep->trace;
   const int Cin = C0 + C1;
   const int Ho = stride == 1 ? H : H / 2, Wo = stride == 1 ? W : W / 2;
   const int bn = pick_bn(Cout, 0, bn_hint);
   int bw, bh, nb;
   conv_tile_box(Ho, Wo, &bw, &bh, &nb);
-  const bool pair = want_pair(((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * ((B + nb - 1) / nb), (Cout + bn - 1) / bn, bn, 1);
+  const bool pair = want_pair(ep->pair_mode, ((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * ((B + nb - 1) / nb), (Cout + bn - 1) / bn, bn, 1);
   p.bw = bw; p.bh = bh; p.nb = nb;
   p.tiles_w = (Wo + bw - 1) / bw;
   p.tiles_h = (Ho + bh - 1) / bh;

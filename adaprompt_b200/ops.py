@@ -64,7 +64,36 @@ def _epilogue(out: torch.Tensor, bias=None, rowbias=None, rows_per_group=0, resi
     if gn_stats is not None:
         _chk(gn_stats, torch.float32, "gn_stats")
     ep.gn_stats = _p(gn_stats)
+    ep.pair_mode = LAUNCH_OPTIONS.pair_mode
+    ep.trace = _p(LAUNCH_OPTIONS.trace)
     return ep
+
+
+class _LaunchOptions:
+    """Per-call options of af_gemm_bf16 / af_conv3x3_bf16 that the host mirror leaves at their defaults; tests and the
+    measurement scripts override them for a `with launch_options(...)` block.  The state lives HERE, in the Python
+    caller - the library itself keeps none."""
+    pair_mode = 0      # AF_PAIR_AUTO
+    trace = None       # device int64 tensor: GEMM timeline probe
+
+
+LAUNCH_OPTIONS = _LaunchOptions()
+
+
+class launch_options:
+    def __init__(self, pair_mode: Optional[int] = None, trace: Optional[torch.Tensor] = None):
+        self.new = (pair_mode, trace)
+
+    def __enter__(self):
+        self.old = (LAUNCH_OPTIONS.pair_mode, LAUNCH_OPTIONS.trace)
+        if self.new[0] is not None:
+            LAUNCH_OPTIONS.pair_mode = int(self.new[0])
+        LAUNCH_OPTIONS.trace = self.new[1]
+        return self
+
+    def __exit__(self, *exc):
+        LAUNCH_OPTIONS.pair_mode, LAUNCH_OPTIONS.trace = self.old
+        return False
 
 
 def gemm(a0: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, *, a1: Optional[torch.Tensor] = None,

@@ -198,6 +198,8 @@ def parse_args(argv=None):
     p.add_argument("--zs_out_id_embs_scale_range", type=float, nargs=2, default=[1.0, 1.0])                 # :269
     p.add_argument("--no_cuda_graph", action="store_true")
     p.add_argument("--save_latents", action="store_true", help="also torch.save the latents next to the images")
+    p.add_argument("--save_conditioning", action="store_true",
+                   help="also torch.save the conditioning tensors (c, uc) and x_T of every batch (parity checks)")
     p.add_argument("--synthetic", action="store_true", help="random-init weights + hashing tokenizer (no files needed)")
     p.add_argument("--synthetic_clip_layers", type=int, default=12)
     p.add_argument("--seed_weights", type=int, default=1234)
@@ -268,6 +270,9 @@ def run(args) -> List[str]:
         all_imgs.append(x)
         if args.save_latents:
             torch.save(samples.cpu(), os.path.join(args.outdir, "samples", f"r{rank}-{b0 + start:05d}-latents.pt"))
+        if args.save_conditioning:
+            torch.save({"c": c[0].cpu(), "uc": uc[0].cpu(), "x_T": x_T.cpu(), "prompts": texts},
+                       os.path.join(args.outdir, "samples", f"r{rank}-{b0 + start:05d}-cond.pt"))
     if all_imgs:
         save_grid(torch.cat(all_imgs), os.path.join(args.outdir, f"grid-r{rank}.png"), args.n_rows or args.n_samples)
     if world > 1:

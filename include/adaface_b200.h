@@ -28,10 +28,13 @@
 extern "C" {
 #endif
 
-#define AF_VERSION 100
+#define AF_VERSION 200
 #define AF_DTYPE_F32 0
 #define AF_DTYPE_BF16 1
 #define AF_GN_MAX_CHUNKS 64
+#define AF_PAIR_AUTO 0
+#define AF_PAIR_NEVER 1
+#define AF_PAIR_ALWAYS 2
 
 typedef struct CUstream_st* af_stream_t; /* == cudaStream_t */
 
@@ -58,6 +61,13 @@ typedef struct af_epilogue {
                              slot per 32 consecutive output rows (GEMM: slot = row / 32, rows-per-sample must be a
                              multiple of 32; conv: af_conv3x3_gn_slots() slots per sample).  Feeds af_groupnorm_finalize
                              so the GroupNorm that consumes this tensor never re-reads it for statistics. */
+  int pair_mode;          /* tile schedule: AF_PAIR_AUTO (0) = CTA pairs (tcgen05 cta_group::2: two SMs share one 256-row tile and
+                             each stages half of the weight tile) where measured to win (linear GEMMs, N tile >= 160, >= 2
+                             waves), AF_PAIR_NEVER, AF_PAIR_ALWAYS (wherever legal).  Results are bit-identical between the
+                             schedules (same accumulation order). */
+  long long* trace;       /* NULL, or a caller-owned device buffer of >= 4*32*8 int64: timeline probe (measurement aid, results
+                             unaffected) - CTA 0 records clock64 stamps [actor: TMA producer, MMA issuer, epilogue warp 0,
+                             extra epilogue stamps][its first 32 tiles][8 events] */
 } af_epilogue;
 
 /* D[M,N] = [A0 | A1][M, K0+K1] . Wt[N, K0+K1]^T, bf16 operands (row-major, K contiguous), fp32 accumulate.
@@ -66,19 +76,6 @@ typedef struct af_epilogue {
  * bn_hint: 0 = auto, or 64/128/160/256 (N tile). */
 int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* A1, long long lda1, int K1, const void* Wt,
                  int M, int N, const af_epilogue* ep, int bn_hint, af_stream_t stream);
-
-/* Tile schedule of af_gemm_bf16 / af_conv3x3_bf16: CTA pairs (tcgen05 cta_group::2: two SMs share one 256-row tile and
- * each stages half of the weight tile) vs single-CTA 128-row tiles.  0 = never pair, 1 (default) = pair where it was
- * measured to win (linear GEMMs, N tile >= 160, >= 2 waves), 2 = pair wherever legal.  Returns the previous mode.
- * Results are bit-identical between the modes (same accumulation order). */
-int af_gemm_set_pair_mode(int mode);
-/* Timeline probe of af_gemm_bf16 / af_conv3x3_bf16 (measurement aid, results unaffected): with a non-null
- * device_buffer (>= 4*32*8 int64, caller-owned; the 4th actor holds extra epilogue stamps) CTA 0 of every following launch records clock64 stamps
- * [actor: TMA producer, MMA issuer, epilogue warp 0][its first 32 tiles][8 events]
- * (producer: tile begin, first stage issued, last stage issued; MMA: begin, accumulator free, first stage landed, tile
- * committed, cycles of the K loop spent waiting for operands; epilogue: tile begin, accumulator full, first chunk in registers, first chunk in smem, first store issued,
- * tile done).  Null switches it off. */
-int af_gemm_set_trace(long long* device_buffer);
 
 /* 3x3 convolution, pad 1, stride 1 or 2, NHWC bf16 input(s) [B,H,W,C0] (+ [B,H,W,C1] concat), weights
  * Wt[Cout][ky][kx][C0+C1] bf16, as an implicit GEMM (no im2col buffer).  Output rows are output pixels

@@ -19,7 +19,9 @@ for _ in range(10): f()
 e1.record(); torch.cuda.synchronize()
 print(f"M{M} N{N} K{K} res={res} f32={f32}: {e0.elapsed_time(e1) * 100:.1f} us per launch")
 buf = torch.zeros(4 * 32 * 8, dtype=torch.int64, device="cuda")
-lib.af_gemm_set_trace(buf.data_ptr()); f(); torch.cuda.synchronize(); lib.af_gemm_set_trace(None)
+with ops.launch_options(trace=buf):
+    f()
+torch.cuda.synchronize()
 t = buf.cpu().view(4, 32, 8)
 t0 = int(t[t > 0].min())
 names = (("prod", 3), ("mma", 4), ("epi", 6))

@@ -526,14 +526,11 @@ def test_gemm_pair_mode_matches_single_cta(M, N, K, res, bf16out):
     bias = _rand(N, seed=3)
     r = _rand(M, N, seed=4) if res else None
     outs = []
-    for mode in (2, 0):
-        old = lib.af_gemm_set_pair_mode(mode)
-        try:
+    for mode in (2, 1):          # AF_PAIR_ALWAYS, AF_PAIR_NEVER (per-call option af_epilogue.pair_mode)
+        with ops.launch_options(pair_mode=mode):
             out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16 if bf16out else torch.float32)
             ops.gemm(a, w, out, bias=bias, residual=r)
             outs.append(out)
-        finally:
-            lib.af_gemm_set_pair_mode(old)
     assert torch.equal(outs[0], outs[1])
     ref = a.float() @ w.float().t() + bias + (r if res else 0)
     assert _rel(outs[0], ref) < (4e-3 if bf16out else 2e-5)
@@ -550,16 +547,13 @@ def test_conv_and_geglu_pair_mode_match_single_cta():
     wg, bg = pack_geglu(_rand(2560, 320, seed=4, scale=320 ** -0.5), _rand(2560, seed=6))
     wg = wg.to(torch.bfloat16).contiguous()
     outs = []
-    for mode in (2, 0):
-        old = lib.af_gemm_set_pair_mode(mode)
-        try:
+    for mode in (2, 1):
+        with ops.launch_options(pair_mode=mode):
             o1 = torch.empty(3, 24, 24, 320, device=DEV)
             st = ops.gn_stats_for_conv(3, 24, 24, 320, DEV)
             ops.conv3x3(x, w, o1, residual=res, gn_stats=st.buf)
             o2 = torch.empty(2048, 1280, device=DEV, dtype=torch.bfloat16)
             ops.gemm(a, wg, o2, bias=bg, geglu=True)
             outs.append((o1, st.buf.clone(), o2))
-        finally:
-            lib.af_gemm_set_pair_mode(old)
     for u, v in zip(*outs):
         assert torch.equal(u, v)

@@ -117,17 +117,13 @@ def test_unet_conv_attention_and_capture_vs_reference_golden(unet):
 def test_unet_batch16_pair_mode_on_off_bit_identical(unet):
     """cta_group::2 pair tiles (auto-enabled at batch 16) vs single-CTA tiles over the WHOLE UNet: same accumulation
     order, so the eps must be bit-identical."""
-    from adaprompt_b200 import _lib
+    from adaprompt_b200 import ops
     from oracle.golden_inputs import unet_inputs
     x, t, ctx, extra = unet_inputs("b16_t501_64")
-    lib = _lib.load()
     with torch.no_grad():
         a = unet(x.cuda(), t.cuda(), context=ctx.cuda(), extra_info=_cuda_extra(extra)).clone()
-        old = lib.af_gemm_set_pair_mode(0)
-        try:
+        with ops.launch_options(pair_mode=1):          # AF_PAIR_NEVER
             b = unet(x.cuda(), t.cuda(), context=ctx.cuda(), extra_info=_cuda_extra(extra)).clone()
-        finally:
-            lib.af_gemm_set_pair_mode(old)
     assert torch.equal(a, b)
 
 

@@ -117,3 +117,36 @@ def test_txt2img_cli_end_to_end_synthetic(tmp_path):
     assert Image.open(str(tmp_path / "grid-r0.png")).size == (512, 256)
     lat = torch.load(str(tmp_path / "samples" / "r0-00000-latents.pt"))
     assert lat.shape == (2, 4, 32, 32) and torch.isfinite(lat).all()
+
+
+def test_txt2img_cli_output_matches_the_oracle_pipeline(tmp_path):
+    """Row N3, checked against the checker: with the conditioning the CLI built (saved by --save_conditioning), the fp32
+    oracle chain - DDIM with annealed CFG on the UNet oracle, then the first-stage decoder oracle - must reproduce the
+    latents the CLI saved (rel-L2 < 2e-2, north_star) and the PNG it wrote (mean |diff| < 2 grey levels)."""
+    import numpy as np
+    from PIL import Image
+    from adaprompt_b200 import txt2img
+    from adaprompt_b200.weights import synth_state_dict
+    from oracle.golden_inputs import EXTRA_INFO
+    from oracle.unet_oracle import UNetSpec, ddim_sample, unet_forward
+    from oracle.vae_oracle import VAESpec, decode_first_stage as oracle_decode
+    txt2img.main(["--synthetic", "--synthetic_clip_layers", "2", "--prompt", "a photo of a z", "--ddim_steps", "4",
+                  "--n_samples", "1", "--H", "256", "--W", "256", "--scale", "4", "1", "--outdir", str(tmp_path),
+                  "--save_latents", "--save_conditioning", "--seed_weights", "1234"])
+    lat = torch.load(str(tmp_path / "samples" / "r0-00000-latents.pt"))
+    cond = torch.load(str(tmp_path / "samples" / "r0-00000-cond.pt"))
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    uspec, vspec = UNetSpec(), VAESpec()
+    sd_u = synth_state_dict(uspec.state_spec(), 1234)
+    sd_v = synth_state_dict(vspec.state_spec(), 1235)
+    apply = lambda x, t, c: unet_forward(sd_u, uspec, x, t, c[0], dict(c[2]))
+    with torch.no_grad():
+        ref_lat, _ = ddim_sample(apply, 4, [1, 4, 32, 32], (cond["c"], ["p"], dict(EXTRA_INFO)),
+                                 (cond["uc"], [""], dict(EXTRA_INFO)), (4.0, 1.0), cond["x_T"])
+        ref_img = torch.clamp((oracle_decode(sd_v, vspec, ref_lat) + 1.0) / 2.0, 0.0, 1.0)
+    e = _rel(lat, ref_lat)
+    png = np.asarray(Image.open(str(tmp_path / "samples" / "r0-00000.png"))).astype(np.float32)
+    ref_png = (255.0 * ref_img[0].permute(1, 2, 0).numpy()).round().clip(0, 255)
+    mad = float(np.abs(png - ref_png).mean())
+    print(f"txt2img vs oracle pipeline: latent rel-L2 {e:.3e}, PNG mean abs diff {mad:.2f} / 255")
+    assert e < 2e-2 and mad < 2.0
