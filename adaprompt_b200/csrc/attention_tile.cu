@@ -19,8 +19,8 @@
 //     F2FP and half an FMNMX3;
 //   * no run-time options, probes or generic-address shared-memory accesses in the loop.
 //
-//   warp 0      TMA producer (Q once; K / V ring)          warp 1   MMA issuer (S_{j+1} early, then PV_j)
-//   warps 2, 3  idle (setmaxnreg works per warpgroup)      warps 4-7 softmax, one thread per query row (TMEM lane = row)
+//   warp 0      TMA producer (Q once; K / V ring)          warp 1   S issuer (S_{j+1} early)    warp 2   PV issuer
+//   warp 3      idle (setmaxnreg works per warpgroup)      warps 4-7 softmax, one thread per query row (TMEM lane = row)
 // P goes to the PV MMA through tensor memory (tcgen05.st, A operand in TMEM).
 #include <type_traits>
 #include <math.h>
@@ -217,13 +217,24 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
         }
       }
     } else if (warp == 1) {
-      // ------------------------------------------------------------------ MMA issuer (whole warp walks the chain,
-      // one elected lane issues): S_0, then per key block S_{j+1} as soon as S_j has been copied out, then PV_j
+      // ------------------------------------------------------------------ S issuer (whole warp walks the chain, one
+      // elected lane issues): S_0, then S_{j+1} as soon as S_j has been copied out.  The PV MMAs have their own issuer
+      // warp: the two chains touch different TMEM columns and are ordered by the barriers alone, and each walks half as
+      // many waits per key block as one combined issuer did (its ~1400 serial cycles per block were the non-ex2 floor
+      // of the kernel, profiles/r02_attention.md).
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, DV);
       const uint32_t q_addr = smem_base + S::kQOff;
-      const uint32_t tm_s = tmem_base + C::kTmemS, tm_o = tmem_base + C::kTmemO, tm_p = tmem_base + C::kTmemP;
-      auto issue_s = [&](int kslot) {
+      const uint32_t tm_s = tmem_base + C::kTmemS;
+      mbar_wait_lean(q_full, 0);
+      int kslot = 0;
+      uint32_t kph = 0;
+      for (int j = 0; j < n_blocks; ++j) {
+        stamp(2, j, 0);
+        mbar_wait_lean(&k_full[kslot], kph);
+        stamp(2, j, 1);
+        if (j > 0) mbar_wait_lean(s_free, (j - 1) & 1);
+        tc_fence_after();
+        stamp(2, j, 2);
         const uint32_t k_addr = smem_base + S::kKOff + kslot * S::kKBytes;
         if (elect_one()) {
 #pragma unroll
@@ -236,25 +247,16 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
           tc_commit(&k_empty[kslot]);
         }
         __syncwarp();
-      };
-      mbar_wait_lean(q_full, 0);
-      mbar_wait_lean(&k_full[0], 0);
-      tc_fence_after();
-      issue_s(0);
-      int kslot = 0, vslot = 0;
-      uint32_t kph = 0, vph = 0;
+        stamp(2, j, 3);
+        if (++kslot == C::KSTAGES) { kslot = 0; kph ^= 1; }
+      }
+    } else if (warp == 2) {
+      // ------------------------------------------------------------------ PV issuer: O += P_j V_j once P_j is in TMEM
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, DV);
+      const uint32_t tm_o = tmem_base + C::kTmemO, tm_p = tmem_base + C::kTmemP;
+      int vslot = 0;
+      uint32_t vph = 0;
       for (int j = 0; j < n_blocks; ++j) {
-        if (j + 1 < n_blocks) {
-          if (++kslot == C::KSTAGES) { kslot = 0; kph ^= 1; }
-          stamp(2, j, 0);
-          mbar_wait_lean(&k_full[kslot], kph);
-          stamp(2, j, 1);
-          mbar_wait_lean(s_free, j & 1);
-          tc_fence_after();
-          stamp(2, j, 2);
-          issue_s(kslot);
-          stamp(2, j, 3);
-        }
         mbar_wait_lean(&v_full[vslot], vph);
         stamp(2, j, 4);
         const uint32_t v_addr = smem_base + S::kVOff + vslot * S::kVBytes;
@@ -297,14 +299,24 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
       tc_fence_after();
       if (tw) stamp(0, j, 1);
       float sc[BN];
-#pragma unroll
-      for (int c = 0; c < BN; c += 32) tile_ld32(s_addr + c, reinterpret_cast<uint32_t*>(sc) + c);
+      // first 32 columns now, the rest in flight under the exponentials of the first chunk (fast path below)
+      tile_ld32(s_addr, reinterpret_cast<uint32_t*>(sc));
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_s_free) : "memory");
-      if (tw) stamp(0, j, 2);
+#pragma unroll
+      for (int c = 32; c < BN; c += 32) tile_ld32(s_addr + c, reinterpret_cast<uint32_t*>(sc) + c);
+      bool s_released = false;
+      auto release_s = [&]() {                    // every column of S_j is in registers: the S issuer may overwrite it
+        if (!s_released) {
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_s_free) : "memory");
+          s_released = true;
+        }
+      };
       if constexpr (MASKED) {
+        release_s();
+        if (tw) stamp(0, j, 2);
         // keep-bits of the block's keys, 32 per ballot (lane l probes key key0 + c + l), then compile-time bit tests
         const int key0 = j * BN;
 #pragma unroll
@@ -317,47 +329,30 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
           for (int e = 0; e < 32; ++e) sc[c + e] = ((keep >> e) & 1u) ? sc[c + e] : -INFINITY;
         }
       }
-      float mx8[8];   // eight independent 3-input max chains
+      auto block_max = [&]() {
+        float mx8[8];   // eight independent 3-input max chains
 #pragma unroll
-      for (int c = 0; c < 8; ++c) mx8[c] = fmaxf(sc[2 * c], sc[2 * c + 1]);
+        for (int c = 0; c < 8; ++c) mx8[c] = fmaxf(sc[2 * c], sc[2 * c + 1]);
 #pragma unroll
-      for (int e = 16; e < BN; e += 16)
+        for (int e = 16; e < BN; e += 16)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) mx8[c] = fmaxf(mx8[c], fmaxf(sc[e + 2 * c], sc[e + 2 * c + 1]));
-      const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
-                             fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
-      float alpha = 1.0f;
-      if (mx > m_ref + kWindow) {               // also the first finite maximum (m_ref == -inf)
-        const float m_new = (m_ref == -INFINITY && fabsf(mx) <= kWindow) ? 0.f : mx;
-        alpha = fast_exp2(m_ref - m_new);       // 0 when m_ref == -inf
-        m_ref = m_new;
-      }
-      const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
-      // O (and its row-sum column) is corrected once every MMA of PV_{j-1} has landed - before P_j is handed over, so no
-      // PV MMA of this block can have been issued yet
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-        mbar_wait_lean(a_pv_done, par ^ 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < DV; c += 16) {
-          uint32_t o[16];
-          tmem_ld16(o_addr + c, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-          tile_st16(o_addr + c, o);
+          for (int c = 0; c < 8; ++c) mx8[c] = fmaxf(mx8[c], fmaxf(sc[e + 2 * c], sc[e + 2 * c + 1]));
+        return fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                     fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+      };
+      auto wait_p_free = [&]() {                  // the P buffer has been consumed by PV_{j-1}
+        if (j > 0) {
+          mbar_wait_lean(a_pv_done, par ^ 1);
+          tc_fence_after();
         }
-        tmem_st_wait();
-      }
-      if (tw) stamp(0, j, 3);
-      if (j > 0) {                                // the P buffer has been consumed by PV_{j-1}
-        mbar_wait_lean(a_pv_done, par ^ 1);
-        tc_fence_after();
-      }
-      if (tw) stamp(0, j, 4);
-      auto exp_block = [&](auto sub) {          // sub: subtract the reference (general) or not (reference 0)
+      };
+      auto exp_block = [&](auto sub, float m_use) {   // sub: subtract the reference (general) or not (reference 0)
 #pragma unroll
         for (int c = 0; c < BN; c += 32) {
+          if (c == 32) {                              // chunk 0 is queued on the ex2 unit: now collect the other loads
+            release_s();
+            if (tw) stamp(0, j, 2);
+          }
           uint32_t pk[16];
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
@@ -368,8 +363,49 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
           tile_st16(pt_addr + c / 2, pk);
         }
       };
-      if (__all_sync(0xffffffffu, m_ref == 0.f)) exp_block(std::false_type{});
-      else exp_block(std::true_type{});
+      // Fast path (the reference is 0 in every row of the warp - always, after the first block, for UNet scores): the
+      // exponentials do not depend on the block maximum, so they are issued straight away and the maximum is only the
+      // overflow guard, computed next to them (ALU pipe under the MUFU queue) instead of in front of them.  A guard trip
+      // re-does the block on the general path (P is rewritten before it is handed over).
+      bool fast = __all_sync(0xffffffffu, m_ref == 0.f);
+      if (fast) {
+        if (tw) stamp(0, j, 3);
+        wait_p_free();
+        if (tw) stamp(0, j, 4);
+        exp_block(std::false_type{}, 0.f);
+        fast = !__any_sync(0xffffffffu, block_max() > kWindow);
+      }
+      if (!fast) {
+        release_s();
+        const float mx = block_max();
+        float alpha = 1.0f;
+        if (mx > m_ref + kWindow) {               // also the first finite maximum (m_ref == -inf)
+          const float m_new = (m_ref == -INFINITY && fabsf(mx) <= kWindow) ? 0.f : mx;
+          alpha = fast_exp2(m_ref - m_new);       // 0 when m_ref == -inf
+          m_ref = m_new;
+        }
+        const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+        // O (and its row-sum column) is corrected once every MMA of PV_{j-1} has landed - before P_j is handed over, so no
+        // PV MMA of this block can have been issued yet
+        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+          mbar_wait_lean(a_pv_done, par ^ 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < DV; c += 16) {
+            uint32_t o[16];
+            tmem_ld16(o_addr + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tile_st16(o_addr + c, o);
+          }
+          tmem_st_wait();
+        }
+        if (tw) stamp(0, j, 3);
+        wait_p_free();
+        if (tw) stamp(0, j, 4);
+        exp_block(std::true_type{}, m_use);
+      }
       if (tw) stamp(0, j, 5);
       tmem_st_wait();
       tc_fence_before();
@@ -481,7 +517,13 @@ int attention_tile_dispatch(const void* Q, long long ldq, const void* K, long lo
   p.out = static_cast<__nv_bfloat16*>(O);
   p.ldo = static_cast<long long>(heads) * d;
   // d = 40: every third exponential on the FMA pipe (0.764 -> 0.688 ms at N = 4096, profiles/r02_attention.md)
-  return d == 40 ? launch_tile<40, 3>(p, stream) : launch_tile<80, 0>(p, stream);
+#ifndef AF_TILE_POLY40
+#define AF_TILE_POLY40 3
+#endif
+#ifndef AF_TILE_POLY80
+#define AF_TILE_POLY80 0
+#endif
+  return d == 40 ? launch_tile<40, AF_TILE_POLY40>(p, stream) : launch_tile<80, AF_TILE_POLY80>(p, stream);
 }
 
 }  // namespace af
