@@ -120,7 +120,7 @@ def cpu_oracle_pair_seconds(reps: int, warmup: int):
     return times[len(times) // 2], times, cores
 
 
-def run_reference(args):
+def run_reference(args, emit=lambda line: print(json.dumps(line))):
     """--impl reference: the reference algorithm (fp32 oracle port of UNetModel + DDIM/CFG arithmetic) on the host
     cores.  Each step is a bounded sample of the workload: one CFG-pair UNet evaluation (UNet batch 2 = one image's
     denoising step); a 512^2 DDIM-50 image costs 50 of them, so images/s = 1 / (50 * t_pair) - an EXTRAPOLATION from the
@@ -143,7 +143,7 @@ def run_reference(args):
                                    f"median {med:.2f} s; x50 DDIM steps per image (extrapolated)"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def gpu_oracle_legs(dev, unet, sampler_call, dev_in, extra, b):
@@ -270,8 +270,17 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the Stage-1 training leg (train_step key)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity gate / GPU eager baseline legs")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON record): anything a library prints there (NCCL's version banner on the
+    # first communicator, ...) is sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import torch
     import torch.distributed as dist
@@ -518,7 +527,7 @@ def main():
             "gpu_eager_baseline": oracle_legs.get("gpu_eager_baseline"),
             "train_step": train_info,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
