@@ -16,13 +16,15 @@ def timeit(f, nbytes, name):
     ms = tot / reps
     print(f"{name:40s} {ms*1e3:8.1f} us  {nbytes/ms/1e6:8.1f} GB/s", flush=True)
 B = 16
-for HW, C in ((4096, 320), (4096, 640), (4096, 960), (1024, 640), (1024, 1280), (256, 1280), (256, 2560), (64, 1280)):
-    x = torch.randn(B, HW, C, device="cuda")
-    st = ops.groupnorm_stats(x.view(B, int(HW ** 0.5), int(HW ** 0.5), C))
+for HW, C in ((4096, 320), (4096, 640), (4096, 960), (1024, 640), (1024, 1280), (1024, 1920), (256, 1280), (256, 2560), (64, 1280), (64, 2560)):
+    side = int(HW ** 0.5)
+    x = torch.randn(B, side, side, C, device="cuda")
+    slots = HW // 32                                  # what a GEMM / conv epilogue produces (one slot per 32 rows)
+    xs = x.view(B, slots, 32, C)
+    st = ops.GNStats(torch.stack((xs.sum(2), (xs * xs).sum(2)), dim=-1).contiguous().view(-1), slots, C)
     g, b = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
-    y = torch.empty(B, int(HW ** 0.5), int(HW ** 0.5), C, device="cuda", dtype=torch.bfloat16)
-    xv = x.view(B, int(HW ** 0.5), int(HW ** 0.5), C)
-    timeit(lambda: ops.groupnorm_apply(xv, st, g, b, 1e-5, True, y), B * HW * C * 6, f"groupnorm_apply+silu B{B} HW{HW} C{C}")
+    y = torch.empty(B, side, side, C, device="cuda", dtype=torch.bfloat16)
+    timeit(lambda: ops.groupnorm_apply(x, st, g, b, 1e-5, True, y), B * HW * C * 6, f"groupnorm finalize + apply B{B} HW{HW} C{C}")
 for rows, C in ((65536, 320), (16384, 640), (4096, 1280)):
     x = torch.randn(rows, C, device="cuda")
     g, b = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
