@@ -50,9 +50,26 @@ def gen_gradient_scaler(alpha, debug=False):
 
 
 def _tokenize(tokenizer, text, max_length, device):
-    enc = tokenizer(text, truncation=True, padding="max_length", max_length=max_length, return_tensors="pt")
-    ids = enc["input_ids"] if isinstance(enc, dict) else enc.input_ids
-    return ids.to(device)
+    """Token ids on `device`.  The prompts on this path are constants ("photo of a id person", the 16-comma template), so
+    the ids are uploaded once per (tokenizer, text) and kept on the tokenizer object: a pageable host-to-device copy
+    synchronises the stream, which would stall the training step every micro-batch and cannot be captured into a CUDA
+    graph.  Callers treat the result as read-only."""
+    cache = getattr(tokenizer, "_af_device_ids", None)
+    if cache is None:
+        cache = {}
+        try:
+            tokenizer._af_device_ids = cache
+        except AttributeError:          # a tokenizer without a __dict__: no caching
+            pass
+    key = (text if isinstance(text, str) else tuple(text), max_length, str(device))
+    ids = cache.get(key)
+    if ids is None:
+        enc = tokenizer(text, truncation=True, padding="max_length", max_length=max_length, return_tensors="pt")
+        ids = (enc["input_ids"] if isinstance(enc, dict) else enc.input_ids).to(device)
+        if len(cache) >= 64:
+            cache.clear()
+        cache[key] = ids
+    return ids
 
 
 def arc2face_forward_face_embs(tokenizer, arc2face_text_encoder, face_embs, input_max_length=77,

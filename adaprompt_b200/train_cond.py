@@ -84,15 +84,18 @@ class SpliceRowsFn(Function):
 
     @staticmethod
     def backward(ctx, g):
+        # no data-dependent shapes (torch.nonzero would synchronise the host and break CUDA-graph capture): rows without
+        # the placeholder (first < 0) and positions past the sequence end contribute zeros / keep their gradient
         first, src_index = ctx.saved_tensors
         S, K, D = ctx.src_shape
-        rows = torch.nonzero(first >= 0).flatten()
-        cols = first[rows].long()[:, None] + torch.arange(K, device=g.device)[None]
-        picked = g[rows[:, None], cols]                                   # [R', K, D]
+        R, N = g.shape[0], g.shape[1]
+        pos = first.long().clamp_min(0)[:, None] + torch.arange(K, device=g.device)[None]            # [R, K]
+        valid = ((first >= 0)[:, None] & (pos < N))[..., None]                                      # [R, K, 1]
+        idx = pos.clamp_max(N - 1)[..., None].expand(R, K, D)
+        picked = g.gather(1, idx)                                                                   # [R, K, D]
         dsrc = torch.zeros(S, K, D, dtype=g.dtype, device=g.device)
-        dsrc.index_add_(0, src_index[rows].long(), picked)
-        dd = g.clone()
-        dd[rows[:, None], cols] = 0
+        dsrc.index_add_(0, src_index.long(), torch.where(valid, picked, torch.zeros_like(picked)))
+        dd = g.scatter(1, idx, torch.where(valid, torch.zeros_like(picked), picked))
         return dd, dsrc, None, None
 
 
@@ -213,10 +216,14 @@ def sbg_forward_train(sbg, arc2face_id_embs: torch.Tensor, out_id_embs_scale: fl
 
 
 def conditioning_train(frozen_tm: CLIPTextTransformer, tokens: torch.Tensor, adaface_subj_embs: torch.Tensor,
-                       placeholder_token: int, K: int = 16, dedup: bool = True) -> torch.Tensor:
+                       placeholder_token: int, K: int = 16, dedup: bool = True,
+                       layers_identical: Optional[bool] = None) -> torch.Tensor:
     """EmbeddingManager.forward + FrozenCLIPEmbedder with grad w.r.t. adaface_subj_embs [BS, 16, K, 768].
     tokens int64 [B, 77] -> c fp32 [16*B, 77, 768] (layer index minor to batch, embedding_manager.py:1349-1353).
-    dedup: encode one of the 16 layer copies when they are identical (always true for the face branch, :558)."""
+    dedup: encode one of the 16 layer copies when they are identical (always true for the face branch, :558);
+    layers_identical: what the caller knows about that by construction (None: compare on the device - one host read).
+    No host synchronisation otherwise: the i-th prompt that holds the placeholder takes subject i mod BS (the
+    reference's repeat to the number of occurrences, :1449-1451), prompts without it pass through the splice."""
     B, N = tokens.shape
     L = N_CA_LAYERS
     tw = frozen_tm.embeddings.token_embedding.weight.detach().float().contiguous()
@@ -224,21 +231,20 @@ def conditioning_train(frozen_tm: CLIPTextTransformer, tokens: torch.Tensor, ada
     emb = ops.gather_rows(tw, tokens.contiguous())                                                 # [B, N, 768]
     first_b = ops.find_first_token(tokens.contiguous(), placeholder_token)                         # [B]
     has = first_b >= 0
-    occurs = int(has.sum().item())
     BS = adaface_subj_embs.shape[0]
-    if occurs and BS < occurs:
-        adaface_subj_embs = adaface_subj_embs.repeat(occurs // BS, 1, 1, 1)                        # :1449-1451
-        BS = adaface_subj_embs.shape[0]
     identical = dedup and adaface_subj_embs.shape[1] == L
     if identical:
-        with torch.no_grad():
-            identical = bool((adaface_subj_embs == adaface_subj_embs[:, :1]).all().item())
+        if layers_identical is None:
+            with torch.no_grad():
+                identical = bool((adaface_subj_embs == adaface_subj_embs[:, :1]).all().item())
+        else:
+            identical = bool(layers_identical)
     w = frozen_tm.last_layers_skip_weights
     if identical:
         rank = (torch.cumsum(has.int(), 0) - 1).clamp_min(0).to(torch.int32)
         src = adaface_subj_embs[:, 0, :K].contiguous()                                             # [BS, K, 768]
         src_index = (rank % BS).contiguous()
-        spliced = SpliceRowsFn.apply(emb, src, first_b, src_index) if occurs else emb
+        spliced = SpliceRowsFn.apply(emb, src, first_b, src_index)
         z = clip_encode_train(frozen_tm, spliced + pos[None, :N], w, trainable=False)
         return z.unsqueeze(1).expand(B, L, N, z.shape[-1]).reshape(B * L, N, z.shape[-1])
     emb16 = emb.unsqueeze(1).repeat(1, L, 1, 1).view(B * L, N, -1)
@@ -247,7 +253,7 @@ def conditioning_train(frozen_tm: CLIPTextTransformer, tokens: torch.Tensor, ada
     rank16 = (torch.cumsum(has16.int(), 0) - 1).clamp_min(0).to(torch.int32)
     src = adaface_subj_embs.reshape(BS * adaface_subj_embs.shape[1], *adaface_subj_embs.shape[2:])[:, :K].contiguous()
     src_index = (rank16 % src.shape[0]).contiguous()
-    spliced = SpliceRowsFn.apply(emb16, src, first16, src_index) if occurs else emb16
+    spliced = SpliceRowsFn.apply(emb16, src, first16, src_index)
     return clip_encode_train(frozen_tm, spliced + pos[None, :N], w, trainable=False)
 
 
@@ -364,19 +370,26 @@ class DistillStep:
         self.unet, self.frozen_tm, self.sbg = unet, frozen_tm, sbg
         self.arc2face, self.tokenizer = arc2face_text_encoder, tokenizer
         self.acp = torch.as_tensor(alphas_cumprod, dtype=torch.float32)
+        self._acp_dev = {}
         self.placeholder_token = placeholder_token
         self.extra_info = dict(extra_info or {"use_layerwise_context": True, "use_conv_attn_kernel_size": -1,
                                               "placeholder2indices": None, "is_training": True})
 
+    def _acp(self, device) -> torch.Tensor:
+        a = self._acp_dev.get(device)
+        if a is None:                      # one upload: a pageable host-to-device copy synchronises the stream every time
+            a = self._acp_dev[device] = self.acp.to(device)
+        return a
+
     def q_sample(self, x0, t, noise):
-        a = self.acp.to(x0.device)[t].view(-1, 1, 1, 1)
+        a = self._acp(x0.device)[t].view(-1, 1, 1, 1)
         return a.sqrt() * x0 + (1 - a).sqrt() * noise
 
     def context(self, face_embs: torch.Tensor, tokens: torch.Tensor) -> torch.Tensor:
         with torch.no_grad():
             _, id_embs = arc2face_forward_face_embs(self.tokenizer, self.arc2face, face_embs)     # embedding_manager.py:1424
-        subj, _ = sbg_forward_train(self.sbg, id_embs)
-        return conditioning_train(self.frozen_tm, tokens, subj, self.placeholder_token)
+        subj, _ = sbg_forward_train(self.sbg, id_embs)       # 16 identical layer copies by construction (:558)
+        return conditioning_train(self.frozen_tm, tokens, subj, self.placeholder_token, layers_identical=True)
 
     @torch.no_grad()
     def teacher_eps(self, x0, t, noise, face_embs) -> torch.Tensor:
@@ -386,7 +399,7 @@ class DistillStep:
             raise RuntimeError("DistillStep: the batch has no teacher_eps and no teacher model was given")
         prompt_embs, _ = arc2face_forward_face_embs(self.tokenizer, self.arc2face, face_embs, input_max_length=21,
                                                     return_full_and_core_embs=True)
-        ddpm = _QSampleOnly(self.acp.to(x0.device))
+        ddpm = _QSampleOnly(self._acp(x0.device))
         preds, _, _, _ = self.teacher(ddpm, x0, noise, t, prompt_embs, num_denoising_steps=1)
         return preds[0]
 
@@ -414,7 +427,7 @@ class DistillStep:
         with torch.no_grad():
             prompt_embs, _ = arc2face_forward_face_embs(self.tokenizer, self.arc2face, face_embs, input_max_length=21,
                                                         return_full_and_core_embs=True)
-            ddpm = _QSampleOnly(self.acp.to(x0.device))
+            ddpm = _QSampleOnly(self._acp(x0.device))
             preds, pred_x0s, noises, ts = self.teacher(ddpm, x0, noise, t, prompt_embs, num_denoising_steps=ND)
         loss_start_step = max(0, ND - 7 // x0.shape[0])
         c = self.context(face_embs, tokens)
@@ -463,21 +476,88 @@ class DistillStep:
         return float(loss.detach())
 
 
+class GraphedMicroStep:
+    """One WHOLE micro-batch of DistillStep replayed from one CUDA graph: Arc2Face prompt, SubjBasisGenerator and frozen
+    CLIP forward, UNet forward + backward, conditioning backward with every parameter gradient accumulated in place into
+    its GradBucket view.  The conditioning half is ~2000 small launches per micro-batch whose host issue time (22 ms)
+    was twice their device time; nothing on the path reads back to the host (no .item(), no nonzero, token ids cached
+    on the device), so the only per-replay host work is copying the batch into the static buffers.
+    Recaptured when the geometry, the parameter storage (Prodigy re-binds parameters into its bucket at its first
+    step) or a weight pack of a frozen module changes."""
+
+    KEYS = ("x0", "t", "noise", "face_embs", "tokens", "teacher_eps")
+
+    def __init__(self, step: "DistillStep", bucket: GradBucket, accum: int):
+        self.step, self.bucket, self.accum = step, bucket, accum
+        self._g = {}
+
+    def _key(self, batch):
+        from .attention import PackedModule
+        ps = self.bucket.params
+        return (tuple((tuple(batch[k].shape), batch[k].dtype) for k in self.KEYS), ps[0].data_ptr(), ps[-1].data_ptr(),
+                PackedModule.PACK_EPOCH)
+
+    def _build(self, batch):
+        st = {k: batch[k].clone() for k in self.KEYS}
+
+        def run():
+            loss = self.step.loss(st["x0"], st["t"], st["noise"], st["teacher_eps"], st["face_embs"], st["tokens"])
+            (loss / self.accum).backward()
+            return loss.detach()
+
+        for p, v in zip(self.bucket.params, self.bucket.views):
+            p.grad = v                                  # AccumulateGrad then adds in place (captured as kernels)
+        keep = self.bucket.flat.clone()                 # gradients of earlier micro-batches of this optimizer step
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):                          # fills the lazy caches (frozen packs, device token ids)
+                run()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            st["loss"] = run()
+        self.bucket.flat.copy_(keep)
+        st["graph"] = graph
+        return st
+
+    def __call__(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        key = self._key(batch)
+        st = self._g.get(key)
+        if st is None:
+            self._g.clear()                             # one live geometry: a stale capture holds GBs of activations
+            st = self._g[key] = self._build(batch)
+        for k in self.KEYS:
+            st[k].copy_(batch[k])
+        st["graph"].replay()
+        return st["loss"].clone()
+
+
 class Stage1Trainer:
     """One optimizer step of the Stage-1 distillation (training_step ddpm.py:595-633 around guided_denoise :2483-2532):
     `accum` micro-batches -> gradients accumulate in the flat bucket -> one all-reduce (mean over ranks) -> clip by norm
-    0.5 -> Prodigy (ldm/prodigy.py) on the same bucket.  The frozen UNet's forward + backward-to-context runs as one
-    CUDA graph per micro-batch geometry (train.GraphedUNetLoss) unless use_graph=False."""
+    0.5 -> Prodigy (ldm/prodigy.py) on the same bucket.
+    use_graph: "step" (default) - each micro-batch is ONE CUDA graph (GraphedMicroStep); True - only the frozen UNet's
+    forward + backward-to-context is a graph (train.GraphedUNetLoss), the conditioning runs on the eager tape;
+    False - everything eager."""
 
     def __init__(self, step: "DistillStep", params: Sequence[torch.nn.Parameter], world_size: int = 1, group=None,
-                 accum: int = 2, max_grad_norm: float = 0.5, optimizer=None, use_graph: bool = True):
+                 accum: int = 2, max_grad_norm: float = 0.5, optimizer=None, use_graph="step"):
         from .prodigy import Prodigy
         self.step, self.world_size, self.group = step, world_size, group
         self.accum, self.max_grad_norm = accum, max_grad_norm
         self.bucket = GradBucket(params)
         self.optimizer = optimizer if optimizer is not None else Prodigy(self.bucket.params)
         self.use_graph = use_graph
+        self._gstep = GraphedMicroStep(step, self.bucket, accum) if use_graph == "step" else None
         self.allreduce_ms = None
+
+    def _micro(self, b: Dict[str, torch.Tensor]) -> torch.Tensor:
+        if self._gstep is None:
+            return self.step.micro_backward(b, accum=self.accum, use_graph=bool(self.use_graph))
+        if b.get("teacher_eps") is None:            # the teacher (no grad) runs outside the captured micro-step
+            b = dict(b, teacher_eps=self.step.teacher_eps(b["x0"], b["t"], b["noise"], b["face_embs"]))
+        return self._gstep(b)
 
     def optimizer_step(self, batches: Sequence[Dict[str, torch.Tensor]], time_allreduce: bool = False):
         """-> {"loss": 0-d tensor (mean over the micro-batches), "grad_norm": 0-d tensor (before clipping)}."""
@@ -486,7 +566,7 @@ class Stage1Trainer:
         self.bucket.begin_step()
         loss_sum = None
         for b in batches:
-            li = self.step.micro_backward(b, accum=self.accum, use_graph=self.use_graph)
+            li = self._micro(b)
             loss_sum = li if loss_sum is None else loss_sum + li
         if time_allreduce and self.world_size > 1:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -250,7 +250,7 @@ def train_leg(dev, unet, world, rank, steps):
             "collective": "one NCCL all-reduce (SUM -> mean) of the flat fp32 gradient bucket per optimizer step" if world > 1 else None,
             "trainable_params": n_params, "loss": float(out["loss"]), "grad_norm": float(out["grad_norm"]),
             "config": {"workload": "stage1_distill_bs4x2accum_64x64", "micro_batch": 4, "grad_accum": 2,
-                       "optimizer": "Prodigy", "clip_grad_norm": 0.5, "unet_cuda_graph": True,
+                       "optimizer": "Prodigy", "clip_grad_norm": 0.5, "cuda_graph": "one graph per micro-batch (conditioning + UNet forward and backward)",
                        "teacher_eps": "fixed random tensor (SURVEY.md 8(d) config 4)"}}
     del trainer, step, params
     torch.cuda.empty_cache()

@@ -25,7 +25,8 @@ def main():
     ap.add_argument("--bs", type=int, default=4)
     ap.add_argument("--accum", type=int, default=2)
     ap.add_argument("--latent", type=int, default=64)
-    ap.add_argument("--no-graph", action="store_true", help="eager autograd tape for the UNet instead of the CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="eager autograd tape instead of the CUDA graph")
+    ap.add_argument("--unet-graph", action="store_true", help="only the UNet forward + backward as a graph (round-2 first form)")
     ap.add_argument("--breakdown", action="store_true", help="per-entry-point CUDA-event times of one optimizer step (stderr)")
     args = ap.parse_args()
     import torch.distributed as dist
@@ -43,7 +44,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     step, params = stage1_stack(dev)
     n_params = sum(p.numel() for p in params)
-    trainer = Stage1Trainer(step, params, world_size=world, accum=args.accum, use_graph=not args.no_graph)
+    trainer = Stage1Trainer(step, params, world_size=world, accum=args.accum, use_graph=False if args.no_graph else (True if args.unet_graph else "step"))
     g = torch.Generator().manual_seed(100 + rank)
 
     def optimizer_step(time_allreduce=False):
@@ -91,7 +92,7 @@ def main():
                           "config": {"workload": "stage1_distill_bs4x2accum_64x64", "micro_batch": args.bs,
                                      "grad_accum": args.accum, "latent": [4, args.latent, args.latent],
                                      "trainable_params": n_params, "optimizer": "Prodigy", "clip_grad_norm": 0.5,
-                                     "unet_cuda_graph": not args.no_graph,
+                                     "cuda_graph": "none" if args.no_graph else ("unet" if args.unet_graph else "micro-batch"),
                                      "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0},
                           "loss": float(out["loss"]), "grad_norm": float(out["grad_norm"]),
                           "prodigy_d": trainer.optimizer.param_groups[0]["d"],
