@@ -34,6 +34,9 @@ class AfEpilogue(Structure):
         ("gn_stats", c_void_p),
         ("pair_mode", c_int),
         ("trace", c_void_p),
+        ("splitk_ws", c_void_p),
+        ("splitk_ws_bytes", c_longlong),
+        ("split_k", c_int),
     ]
 
 
@@ -132,6 +135,9 @@ class AdaFaceB200Error(RuntimeError):
     pass
 
 
+ABI_VERSION = 201      # include/adaface_b200.h AF_VERSION
+
+
 def load():
     """Loads the shared library (building is the job of __graft_entry__.build / adaprompt_b200.build)."""
     global _lib
@@ -142,6 +148,10 @@ def load():
             f"{LIB_PATH} not found: build it with `python -m adaprompt_b200.build` (needs nvcc, sm_100a). "
             "There is no CPU fallback.")
     lib = ctypes.CDLL(LIB_PATH)
+    lib.af_version.restype = c_int
+    if lib.af_version() != ABI_VERSION:        # a stale build: struct layouts (af_epilogue) would not match this binding
+        raise AdaFaceB200Error(f"{LIB_PATH} has ABI version {lib.af_version()}, this binding needs {ABI_VERSION}: rebuild "
+                               "with `python -m adaprompt_b200.build`")
     ns = types.SimpleNamespace(_cdll=lib)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol

@@ -111,6 +111,11 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 #ifndef AF_WATCHDOG_NS
 #define AF_WATCHDOG_NS 4000000000ull
 #endif
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   if (mbar_try_wait(addr, parity)) return;

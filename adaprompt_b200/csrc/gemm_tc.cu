@@ -62,6 +62,13 @@ struct GemmParams {
   int act;                 // 0 none, 1 quick_gelu x*sigmoid(1.702x) on (acc + bias), before the residual add
   float* gn_stats;         // [slots_total][N][2] per-channel (sum, sumsq) over 32-row quarters of the output, or null
   int gn_slots;            // conv: stat slots per sample (= tiles_w * tiles_h * bw * bh / 32)
+  // Split-K of the LAST, partial wave of tiles (see "work units" below); split == 1: every unit is a whole tile
+  int dp_tiles;            // tiles [0, dp_tiles) are whole-K units; each tile in [dp_tiles, tiles) is `split` units
+  int split;               // K ranges per remainder tile
+  int kb_per;              // K blocks per range (the last range takes what is left)
+  int num_units;           // dp_tiles + (tiles - dp_tiles) * split
+  float* ws;               // fp32 partial accumulators [(tile - dp_tiles) * (split - 1) + s][chunk][j][128 rows][4]
+  int* ws_flags;           // [(tile - dp_tiles)][2]: partial warps arrived, finisher warps done (zero between launches)
 };
 
 constexpr int kEpiWarps = 8;                    // 2 warps per TMEM lane quarter, each takes every other 32-col chunk
@@ -146,6 +153,34 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     m_tile = CTA2 ? 2 * pm + static_cast<int>(cta_rank) : pm;
   };
 
+  // Work units.  A persistent block walks units u = blockIdx.x, + gridDim.x, ...  Units [0, dp_tiles) are whole tiles
+  // (the full waves).  The tiles of the last, partial wave would leave most SMs idle for a whole tile time (64 tiles on
+  // 148 SMs for the 8x8 convolutions), so each of them is cut into `split` K ranges = `split` units on different
+  // blocks: ranges 0 .. split-2 ("partial" units) dump their fp32 accumulator tile to a workspace and signal; the
+  // unit with the LAST range (the "finisher") waits for them, adds the partials in range order (fixed order:
+  // bit-reproducible) and runs the normal fused epilogue.  A unit only ever waits for units with a smaller index and
+  // every block walks its units in increasing order, so with all blocks resident (grid <= SM count, one block per SM)
+  // the smallest unfinished unit can always proceed: no deadlock.
+  const int num_units = CTA2 ? num_tiles : p.num_units;
+  struct Unit {
+    int tile, kb0, kb1, kind, rt, s;   // kind: 0 whole tile, 1 partial, 2 finisher; rt = tile - dp_tiles
+  };
+  auto unit_at = [&](int u) -> Unit {
+    Unit w;
+    if (CTA2 || u < p.dp_tiles) {
+      w.tile = u; w.kb0 = 0; w.kb1 = p.num_kb; w.kind = 0; w.rt = 0; w.s = 0;
+    } else {
+      const int r = u - p.dp_tiles;
+      w.rt = r / p.split;
+      w.s = r - w.rt * p.split;
+      w.tile = p.dp_tiles + w.rt;
+      w.kb0 = w.s * p.kb_per;
+      w.kb1 = w.s == p.split - 1 ? p.num_kb : w.kb0 + p.kb_per;
+      w.kind = w.s == p.split - 1 ? 2 : 1;
+    }
+    return w;
+  };
+
   // timeline probe: actor 0 = TMA producer, 1 = MMA issuer, 2 = epilogue warp 0 (lane 0 each), CTA 0, first 32 tiles
   const bool tracing = p.trace != nullptr && blockIdx.x == 0 && lane == 0;
   auto stamp = [&](int actor, int tile_no, int ev) {
@@ -195,7 +230,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       constexpr uint32_t kATx = (CTA2 ? 2u : 1u) * Cfg::kABytes, kBTx = (CTA2 ? 2u : 1u) * Cfg::kBBytes;
-      for (int tile = tile_first, tno = 0; tile < num_tiles; tile += tile_step, ++tno) {
+      for (int unit = tile_first, tno = 0; unit < num_units; unit += tile_step, ++tno) {
+        const Unit wu = unit_at(unit);
+        const int tile = wu.tile;
         int n_tile, m_tile;
         tile_mn(tile, n_tile, m_tile);
         if (loads_a) stamp(0, tno, 0);
@@ -211,8 +248,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         // per-stage chain of the producer has no option branches left.
         auto a_loop = [&](auto amode_c) {
           constexpr int AM = decltype(amode_c)::value;
-          int cblk = 0, ky = 0, kx = 0;
-          for (int kb = 0; kb < p.num_kb; ++kb) {
+          int cblk = wu.kb0, ky = 0, kx = 0;
+          if (AM != 0 && wu.kb0 != 0) {               // a K range of a split tile starts inside the (tap, channel) walk
+            const int tap = wu.kb0 / p.cpb;
+            cblk = wu.kb0 - tap * p.cpb;
+            ky = tap / 3;
+            kx = tap - 3 * ky;
+          }
+          for (int kb = wu.kb0; kb < wu.kb1; ++kb) {
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             const bool second = AM == 0 && cblk >= p.kb_split;     // dual-source K only exists for linear GEMMs ...
             const bool second_c = AM == 1 && cblk >= p.kb_split;   // ... and stride-1 convolutions (concat input)
@@ -247,7 +290,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
               stage = 0;
               phase ^= 1;
             }
-            if (kb == 0) stamp(0, tno, 1);
+            if (kb == wu.kb0) stamp(0, tno, 1);
           }
         };
         if (loads_a) {
@@ -255,7 +298,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           else if (p.amode == 1) a_loop(std::integral_constant<int, 1>{});
           else a_loop(std::integral_constant<int, 2>{});
         } else {
-          for (int kb = 0; kb < p.num_kb; ++kb) {
+          for (int kb = wu.kb0; kb < wu.kb1; ++kb) {
             uint8_t* sb = smem + stage * Cfg::kStageBytes + Cfg::kABytes;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (elect_one()) {
@@ -284,19 +327,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = tile_first, tno = 0; tile < num_tiles; tile += tile_step, ++tno) {
+      for (int unit = tile_first, tno = 0; unit < num_units; unit += tile_step, ++tno) {
+        const Unit wu = unit_at(unit);
         stamp(1, tno, 0);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         stamp(1, tno, 1);
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
         long long waited = 0;       // timeline probe only: cycles this tile's K loop spent waiting for operands
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = wu.kb0; kb < wu.kb1; ++kb) {
           const long long w0 = tracing ? clock64() : 0;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (tracing) waited += clock64() - w0;
-          if (kb == 0) stamp(1, tno, 2);
+          if (kb == wu.kb0) stamp(1, tno, 2);
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t adesc = umma_desc_sw128(sa);
           const uint64_t bdesc = umma_desc_sw128(sa + Cfg::kABytes);
@@ -305,7 +349,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             for (int k = 0; k < 4; ++k) {
               // +32 bytes (16 bf16) along K inside the 128B swizzle atom == +2 in the >>4 address field
               if constexpr (CTA2) tc_mma_ss2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-              else tc_mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else tc_mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - wu.kb0) | k) != 0 ? 1u : 0u);
             }
             if constexpr (CTA2) tc_commit2(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
           }
@@ -354,11 +398,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         c3 = tn * p.nb + r0 / (p.bw * p.bh);
       }
     };
-    // residual prefetch cursor: walks this warp's work items (tile, chunk) in order, kAhead items in front
-    int pf_tile = tile_first, pf_i = 0, pf_n = 0, pf_c1 = 0, pf_c2 = 0, pf_c3 = 0, pf_item = 0;
-    if (pf_tile < num_tiles) tile_rows(pf_tile, pf_n, pf_c1, pf_c2, pf_c3);
+    // residual prefetch cursor: walks this warp's work items (output unit, chunk) in order, kAhead items in front.
+    // Partial units of split tiles write no output and read no residual: the cursor skips them.
+    auto is_partial = [&](int u) { return !CTA2 && u >= p.dp_tiles && (u - p.dp_tiles) % p.split != p.split - 1; };
+    int pf_unit = tile_first, pf_i = 0, pf_n = 0, pf_c1 = 0, pf_c2 = 0, pf_c3 = 0, pf_item = 0;
+    auto pf_settle = [&]() {          // first output unit at or after pf_unit, and its row coordinates
+      while (pf_unit < num_units && is_partial(pf_unit)) pf_unit += tile_step;
+      if (pf_unit < num_units) tile_rows(unit_at(pf_unit).tile, pf_n, pf_c1, pf_c2, pf_c3);
+    };
+    pf_settle();
     auto issue_res_load = [&]() {   // lane 0 only
-      if (pf_tile >= num_tiles) return;
+      if (pf_unit >= num_units) return;
       const int sl = pf_item % SLOTS;
       mbar_arrive_expect_tx(&my_res_bar[sl], 4096);
       tma_load_4d(my_slots + sl * Cfg::kSlotBytes, &p.tmRes, &my_res_bar[sl], pf_n * kOutCols + half * 32 + 64 * pf_i,
@@ -366,8 +416,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       ++pf_item;
       if (++pf_i == nch) {
         pf_i = 0;
-        pf_tile += tile_step;
-        if (pf_tile < num_tiles) tile_rows(pf_tile, pf_n, pf_c1, pf_c2, pf_c3);
+        pf_unit += tile_step;
+        pf_settle();
       }
     };
     // All bulk-tensor instructions of this warp (residual loads, stores, group commits / waits) are issued by the lane
@@ -383,7 +433,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     int item = 0;                      // running work-item index of this warp (slot = item % SLOTS)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = tile_first, tno = 0; tile < num_tiles; tile += tile_step, ++tno) {
+    for (int unit = tile_first, tno = 0; unit < num_units; unit += tile_step, ++tno) {
+      const Unit wu = unit_at(unit);
+      const int tile = wu.tile;
       int n_tile, m_tile;
       tile_mn(tile, n_tile, m_tile);
       if (ew == 0) stamp(2, tno, 0);
@@ -421,6 +473,54 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       tc_fence_after();
       if (ew == 0) stamp(2, tno, 1);
       const uint32_t t_acc = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+
+      // split tiles: this thread's float4 group j of 32-column chunk ch lives at ws_row[(ch * 8 + j) * 128] (one
+      // 512-byte run per warp and group: coalesced both ways)
+      float4* ws_row = nullptr;
+      if constexpr (!GEGLU && !CTA2) {
+        if (wu.kind != 0) {
+          constexpr int kTileF4 = 128 * (BN / 4);                              // float4 per partial tile
+          ws_row = reinterpret_cast<float4*>(p.ws) + static_cast<size_t>(wu.rt) * (p.split - 1) * kTileF4 + q * 32 + lane;
+          if (wu.kind == 1) {
+            // ---------------------------------------------------------- partial unit: accumulator -> workspace
+            float4* dst = ws_row + static_cast<size_t>(wu.s) * kTileF4;
+            for (int i = 0; i < nch; ++i) {
+              const int c = half * 32 + 64 * i;
+              uint32_t v[32];
+              tmem_ld32(t_acc + c, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                __stcg(dst + ((c >> 5) * 8 + j) * 128, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+            }
+            __threadfence();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              atomicAdd(p.ws_flags + 2 * wu.rt, 1);
+              mbar_arrive(&tempty_bar[acc]);
+            }
+            if (++acc == 2) {
+              acc = 0;
+              acc_phase ^= 1;
+            }
+            continue;
+          }
+          // ------------------------------------------------------------ finisher: all partial warps have written
+          if (lane == 0) {
+            const int want = (p.split - 1) * kEpiWarps;
+            const volatile int* flag = p.ws_flags + 2 * wu.rt;
+            unsigned long long t0 = 0;
+            while (*flag < want) {
+              if (t0 == 0) t0 = globaltimer_ns();
+              else if (globaltimer_ns() - t0 > AF_WATCHDOG_NS) { printf("gemm_tc: split-K finisher timed out (tile %d)\n", tile); __trap(); }
+            }
+            __threadfence();
+          }
+          __syncwarp();
+        }
+      }
 
       // (Fetching chunk i+1 from TMEM into a second register set while chunk i is staged was measured SLOWER: 48.7 ->
       // 59.4 us on M65536 N320 K320 +res, the conversion phase doubles - profiles/r01_gemm_epilogue_timeline.md.)
@@ -510,6 +610,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             __syncwarp();
           }
           tmem_ld_wait();
+          if (ws_row != nullptr) {   // finisher of a split tile: + the partial accumulators, in K-range order
+            constexpr int kTileF4 = 128 * (BN / 4);
+            for (int sp = 0; sp < p.split - 1; ++sp) {
+              const float4* src = ws_row + static_cast<size_t>(sp) * kTileF4 + (c >> 5) * 8 * 128;
+              float4 part[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) part[j] = __ldcg(src + j * 128);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + part[j].x);
+                v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + part[j].y);
+                v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + part[j].z);
+                v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + part[j].w);
+              }
+            }
+          }
           if (ew == 0 && i == 0) stamp(2, tno, 2);
           // one uniform branch per OPTION, not per element group: with the activation / residual tests inside the
           // unrolled loop the compiler kept 16 taken branches per item (~70 cycles each on this serial chain)
@@ -580,6 +696,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
+        if (ws_row != nullptr) {   // the last finisher warp re-arms the tile's flags for the next launch
+          if (atomicAdd(p.ws_flags + 2 * wu.rt + 1, 1) == kEpiWarps - 1) {
+            p.ws_flags[2 * wu.rt] = 0;
+            p.ws_flags[2 * wu.rt + 1] = 0;
+            __threadfence();
+          }
+        }
         if (CTA2 && !leader) mbar_arrive_cta(&tempty_bar[acc], 0);   // the leader's MMA warp owns both accumulators
         else mbar_arrive(&tempty_bar[acc]);
       }
@@ -632,8 +755,7 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
     cfg.numAttrs = 1;
     AF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, GEGLU, SLOTS, CTA2>, p));
   } else {
-    const int tiles = p.m_tiles * p.n_tiles;
-    const int grid = tiles < num_sms() ? tiles : num_sms();
+    const int grid = p.num_units < num_sms() ? p.num_units : num_sms();
     gemm_tc_kernel<BN, GEGLU, SLOTS, CTA2><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
   }
   AF_LAUNCH_CHECK("gemm_tc_kernel");
@@ -652,6 +774,50 @@ static bool want_pair(int pair_mode, int m_tiles, int n_tiles, int bn, int amode
 template <int BN, bool GEGLU, int SLOTS>
 static int launch_gemm_mode(const GemmParams& p, bool pair, cudaStream_t stream) {
   return pair ? launch_gemm<BN, GEGLU, SLOTS, true>(p, stream) : launch_gemm<BN, GEGLU, SLOTS, false>(p, stream);
+}
+
+// Split-K of the last partial wave (kernel comment "work units").  Cost model in units of one K block of main-loop
+// time, fitted to scripts/bench_splitk.py on B200 (profiles/r02_splitk.md): a unit costs its K blocks + a fixed part
+// (pipeline fill, accumulator hand-over, epilogue), the finisher additionally a serial L2 round trip per partial tile
+// it adds.  A K block of an implicit-GEMM convolution takes about twice as long as one of a linear GEMM, so the fixed
+// parts weigh half as much there.  Picks the split that minimises the critical path; 1 = whole tiles only.
+constexpr int kSplitFlagInts = 4096;          // flag region at the head of the workspace: 2 ints per remainder tile
+constexpr int kMaxSplit = 16;
+static void plan_split(GemmParams& p, int bn, bool pair, const af_epilogue* ep) {
+  const int tiles = p.m_tiles * p.n_tiles;
+  p.dp_tiles = tiles;
+  p.split = 1;
+  p.kb_per = p.num_kb;
+  p.num_units = tiles;
+  p.ws = nullptr;
+  p.ws_flags = nullptr;
+  if (pair || p.geglu || ep->split_k == 1 || ep->splitk_ws == nullptr) return;
+  const int G = num_sms();
+  const int dp = (tiles / G) * G, R = tiles - dp;
+  if (R == 0 || 2 * R > kSplitFlagInts) return;
+  const long long avail = (ep->splitk_ws_bytes - static_cast<long long>(kSplitFlagInts) * 4) / (128ll * bn * 4);   // partial tiles
+  const int kUnitFixed = p.amode != 0 ? 15 : 30, kPartialCost = p.amode != 0 ? 10 : 20;
+  int best = 1;
+  long long best_cost = p.num_kb + kUnitFixed;                 // the remainder wave as whole tiles
+  const int lo = ep->split_k > 1 ? ep->split_k : 2, hi = ep->split_k > 1 ? ep->split_k : kMaxSplit;
+  for (int S = lo; S <= hi; ++S) {
+    const int per = (p.num_kb + S - 1) / S;
+    if (per * (S - 1) >= p.num_kb || per < 2) continue;        // every range needs work; tiny ranges are all overhead
+    if (static_cast<long long>(R) * (S - 1) > avail) continue;
+    const long long rounds = (static_cast<long long>(R) * S + G - 1) / G;
+    const long long cost = rounds * (per + kUnitFixed) + static_cast<long long>(kPartialCost) * (S - 1);
+    if (ep->split_k > 1 || cost < best_cost) {
+      best = S;
+      best_cost = cost;
+    }
+  }
+  if (best == 1) return;
+  p.dp_tiles = dp;
+  p.split = best;
+  p.kb_per = (p.num_kb + best - 1) / best;
+  p.num_units = dp + R * best;
+  p.ws_flags = static_cast<int*>(ep->splitk_ws);
+  p.ws = reinterpret_cast<float*>(static_cast<char*>(ep->splitk_ws) + static_cast<size_t>(kSplitFlagInts) * 4);
 }
 
 static int dispatch_gemm(int bn, const GemmParams& p, bool pair, cudaStream_t stream) {
@@ -797,6 +963,7 @@ extern "C" int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* 
   if (rc) return rc;
   rc = make_epilogue_maps(p, ep->geglu ? N / 2 : N, false);
   if (rc) return rc;
+  plan_split(p, bn, pair, ep);
   return dispatch_gemm(bn, p, pair, stream);
 }
 
@@ -892,5 +1059,6 @@ extern "C" int af_conv3x3_bf16(const void* X0, int C0, const void* X1, int C1, c
   }
   rc = make_epilogue_maps(p, Cout, true);
   if (rc) return rc;
+  plan_split(p, bn, pair, ep);
   return dispatch_gemm(bn, p, pair, stream);
 }

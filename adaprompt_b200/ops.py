@@ -66,7 +66,35 @@ def _epilogue(out: torch.Tensor, bias=None, rowbias=None, rows_per_group=0, resi
     ep.gn_stats = _p(gn_stats)
     ep.pair_mode = LAUNCH_OPTIONS.pair_mode
     ep.trace = _p(LAUNCH_OPTIONS.trace)
+    ep.split_k = LAUNCH_OPTIONS.split_k
+    if not geglu and LAUNCH_OPTIONS.split_k != 1:
+        ws = _splitk_workspace(out.device)
+        if ws is not None:
+            ep.splitk_ws, ep.splitk_ws_bytes = ws.data_ptr(), ws.numel() * 4
     return ep
+
+
+SPLITK_WS_BYTES = 16384 + 48 * (1 << 20)     # flag region + 48 MB of fp32 partial tiles
+_splitk_ws = {}
+
+
+def _splitk_workspace(device) -> Optional[torch.Tensor]:
+    """Split-K workspace (af_epilogue.splitk_ws).  Eager launches: one per (device, stream), because two GEMMs that run
+    concurrently must not share flags.  Launches recorded into a CUDA graph: one per device, shared by all captured
+    graphs (replays are stream-ordered; two graphs of one device must not replay concurrently).  Zeroed once - the
+    kernel leaves the flag region zero.  Nothing is allocated while a capture is in progress: the eager warm-up that
+    precedes every capture creates both; without a workspace the whole-tile schedule runs."""
+    capturing = torch.cuda.is_current_stream_capturing()
+    gkey = (device.index, "graph")
+    if capturing:
+        return _splitk_ws.get(gkey)
+    if gkey not in _splitk_ws:
+        _splitk_ws[gkey] = torch.zeros(SPLITK_WS_BYTES // 4, dtype=torch.float32, device=device)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _splitk_ws.get(key)
+    if ws is None:
+        ws = _splitk_ws[key] = torch.zeros(SPLITK_WS_BYTES // 4, dtype=torch.float32, device=device)
+    return ws
 
 
 class _LaunchOptions:
@@ -75,24 +103,28 @@ class _LaunchOptions:
     caller - the library itself keeps none."""
     pair_mode = 0      # AF_PAIR_AUTO
     trace = None       # device int64 tensor: GEMM timeline probe
+    split_k = 0        # 0 auto, 1 never, n > 1: cut the tiles of the last partial wave into n K ranges
 
 
 LAUNCH_OPTIONS = _LaunchOptions()
 
 
 class launch_options:
-    def __init__(self, pair_mode: Optional[int] = None, trace: Optional[torch.Tensor] = None):
-        self.new = (pair_mode, trace)
+    def __init__(self, pair_mode: Optional[int] = None, trace: Optional[torch.Tensor] = None,
+                 split_k: Optional[int] = None):
+        self.new = (pair_mode, trace, split_k)
 
     def __enter__(self):
-        self.old = (LAUNCH_OPTIONS.pair_mode, LAUNCH_OPTIONS.trace)
+        self.old = (LAUNCH_OPTIONS.pair_mode, LAUNCH_OPTIONS.trace, LAUNCH_OPTIONS.split_k)
         if self.new[0] is not None:
             LAUNCH_OPTIONS.pair_mode = int(self.new[0])
         LAUNCH_OPTIONS.trace = self.new[1]
+        if self.new[2] is not None:
+            LAUNCH_OPTIONS.split_k = int(self.new[2])
         return self
 
     def __exit__(self, *exc):
-        LAUNCH_OPTIONS.pair_mode, LAUNCH_OPTIONS.trace = self.old
+        LAUNCH_OPTIONS.pair_mode, LAUNCH_OPTIONS.trace, LAUNCH_OPTIONS.split_k = self.old
         return False
 
 

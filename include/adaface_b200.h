@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AF_VERSION 200
+#define AF_VERSION 201
 #define AF_DTYPE_F32 0
 #define AF_DTYPE_BF16 1
 #define AF_GN_MAX_CHUNKS 64
@@ -68,7 +68,15 @@ typedef struct af_epilogue {
   long long* trace;       /* NULL, or a caller-owned device buffer of >= 4*32*8 int64: timeline probe (measurement aid, results
                              unaffected) - CTA 0 records clock64 stamps [actor: TMA producer, MMA issuer, epilogue warp 0,
                              extra epilogue stamps][its first 32 tiles][8 events] */
+  void* splitk_ws;        /* NULL (whole-tile schedule only), or a caller-owned device workspace whose first
+                             AF_SPLITK_FLAG_BYTES are ZERO when the call is issued (the kernel leaves them zero again):
+                             the tiles of the last, partial wave are cut into K ranges on different SMs, the partial fp32
+                             accumulators travel through this buffer and are added in K order (bit-reproducible).  One
+                             workspace per stream: two GEMMs running concurrently must not share it. */
+  long long splitk_ws_bytes; /* size of splitk_ws; bounds the number of partial tiles (128 x BN fp32 each) */
+  int split_k;            /* 0 = auto (cost model), 1 = never, n > 1 = cut every remainder tile into n K ranges (tests) */
 } af_epilogue;
+#define AF_SPLITK_FLAG_BYTES 16384
 
 /* D[M,N] = [A0 | A1][M, K0+K1] . Wt[N, K0+K1]^T, bf16 operands (row-major, K contiguous), fp32 accumulate.
  * Replaces nn.Linear (attention.py:35,55,157-165) and 1x1 nn.Conv2d (attention.py:302,313; openaimodel.py:245);

@@ -30,7 +30,7 @@ def test_binding_table_matches_header():
 
 
 def test_version_and_error_string(lib):
-    assert lib.af_version() == 200
+    assert lib.af_version() == 201
     assert isinstance(lib.af_last_error(), bytes)
 
 

@@ -527,7 +527,7 @@ def test_gemm_pair_mode_matches_single_cta(M, N, K, res, bf16out):
     r = _rand(M, N, seed=4) if res else None
     outs = []
     for mode in (2, 1):          # AF_PAIR_ALWAYS, AF_PAIR_NEVER (per-call option af_epilogue.pair_mode)
-        with ops.launch_options(pair_mode=mode):
+        with ops.launch_options(pair_mode=mode, split_k=1):     # whole tiles: a split tile re-associates the K sum
             out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16 if bf16out else torch.float32)
             ops.gemm(a, w, out, bias=bias, residual=r)
             outs.append(out)
@@ -548,7 +548,7 @@ def test_conv_and_geglu_pair_mode_match_single_cta():
     wg = wg.to(torch.bfloat16).contiguous()
     outs = []
     for mode in (2, 1):
-        with ops.launch_options(pair_mode=mode):
+        with ops.launch_options(pair_mode=mode, split_k=1):
             o1 = torch.empty(3, 24, 24, 320, device=DEV)
             st = ops.gn_stats_for_conv(3, 24, 24, 320, DEV)
             ops.conv3x3(x, w, o1, residual=res, gn_stats=st.buf)
@@ -557,3 +557,103 @@ def test_conv_and_geglu_pair_mode_match_single_cta():
             outs.append((o1, st.buf.clone(), o2))
     for u, v in zip(*outs):
         assert torch.equal(u, v)
+
+
+# ------------------------------------------------------------------------------------------------ split-K of the last wave
+def _splitk_flags_clear():
+    from adaprompt_b200 import ops
+    torch.cuda.synchronize()
+    return all(int(ws[:4096].view(torch.int32).abs().sum().item()) == 0 for ws in ops._splitk_ws.values())
+
+
+@pytest.mark.parametrize("M,N,K,bn,res,bf16out,split", [
+    (1024, 1280, 1280, 0, True, False, 0),      # 64 tiles on 148 SMs: the auto plan splits
+    (1024, 1280, 2560, 0, False, False, 5),
+    (4096, 1280, 1280, 0, True, False, 0),      # 256 tiles = one full wave + 108 remainder tiles
+    (4096, 1280, 5120, 0, True, True, 4),
+    (1000, 640, 2560, 128, False, True, 3),     # ragged M, last K range shorter than the others
+    (300, 320, 320, 0, True, False, 2),
+])
+def test_gemm_split_k_matches_whole_tiles(M, N, K, bn, res, bf16out, split):
+    """The K ranges of a split tile are summed in range order: deterministic, equal to the whole-tile schedule up to
+    fp32 re-association (1e-6), flags left clear for the next launch."""
+    from adaprompt_b200 import ops
+    a = _rand(M, K, seed=1, dtype=torch.bfloat16)
+    w = _rand(N, K, seed=2, scale=K ** -0.5, dtype=torch.bfloat16)
+    bias = _rand(N, seed=3)
+    r = _rand(M, N, seed=4) if res else None
+    dt = torch.bfloat16 if bf16out else torch.float32
+    outs = {}
+    for mode in (1, split, split):
+        with ops.launch_options(split_k=mode):
+            out = torch.empty(M, N, device=DEV, dtype=dt)
+            st = ops.gn_stats_for_gemm(1, ((M + 31) // 32) * 32, N, DEV) if (not bf16out and M % 32 == 0) else None
+            ops.gemm(a, w, out, bias=bias, residual=r, bn=bn, gn_stats=st.buf if st else None)
+            outs.setdefault(mode, []).append((out, st.buf.clone() if st else None))
+    whole, (s1, s2) = outs[1][0], outs[split]
+    assert torch.equal(s1[0], s2[0]) and (s1[1] is None or torch.equal(s1[1], s2[1]))        # run-to-run bit-exact
+    ref = a.float() @ w.float().t() + bias + (r if res else 0)
+    assert _rel(s1[0], ref) < (4e-3 if bf16out else 2e-5)
+    assert _rel(s1[0], whole[0]) < (4e-3 if bf16out else 1e-5)
+    if s1[1] is not None:
+        assert _rel(s1[1], whole[1]) < 1e-5
+    assert _splitk_flags_clear()
+
+
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout,stride,split", [
+    (16, 8, 8, 1280, 0, 1280, 1, 0), (16, 8, 8, 1280, 1280, 1280, 1, 9), (16, 16, 16, 1280, 0, 1280, 2, 0),
+    (4, 8, 8, 1280, 0, 1280, 1, 0), (2, 16, 16, 640, 320, 640, 1, 7), (16, 16, 16, 1280, 0, 1280, 1, 0),
+])
+def test_conv_split_k_matches_whole_tiles(B, H, W, C0, C1, Cout, stride, split):
+    from adaprompt_b200 import ops
+    from adaprompt_b200.packing import pack_conv3x3
+    Cin = C0 + C1
+    x0 = _rand(B, H, W, C0, seed=1, dtype=torch.bfloat16)
+    x1 = _rand(B, H, W, C1, seed=2, dtype=torch.bfloat16) if C1 else None
+    wt = _rand(Cout, Cin, 3, 3, seed=3, scale=(9 * Cin) ** -0.5).to(torch.bfloat16)
+    w = pack_conv3x3(wt)
+    bias, emb = _rand(Cout, seed=4), _rand(B, Cout, seed=5)
+    Ho, Wo = H // stride, W // stride
+    res = _rand(B, Ho, Wo, Cout, seed=6)
+    outs = []
+    for mode in (1, split):
+        with ops.launch_options(split_k=mode):
+            out = torch.empty(B, Ho, Wo, Cout, device=DEV)
+            st = ops.gn_stats_for_conv(B, Ho, Wo, Cout, DEV)
+            ops.conv3x3(x0, w, out, x1=x1, stride=stride, bias=bias, rowbias=emb, residual=res,
+                        gn_stats=st.buf if st else None)
+            outs.append((out, st.buf.clone() if st else None))
+    ref = _conv_ref(torch.cat([x0, x1], -1) if C1 else x0, wt, bias, stride) + emb[:, None, None, :] + res
+    assert _rel(outs[1][0], ref) < 2e-5
+    assert _rel(outs[1][0], outs[0][0]) < 5e-5          # fp32 re-association of the K = 9 * Cin sum
+    if outs[0][1] is not None:
+        assert _rel(outs[1][1], outs[0][1]) < 1e-5
+    assert _splitk_flags_clear()
+
+
+def test_split_k_replays_from_a_cuda_graph():
+    from adaprompt_b200 import ops
+    from adaprompt_b200.packing import pack_conv3x3
+    x = _rand(16, 8, 8, 1280, seed=1, dtype=torch.bfloat16)
+    w = pack_conv3x3(_rand(1280, 1280, 3, 3, seed=2, scale=(9 * 1280) ** -0.5).to(torch.bfloat16))
+    out = torch.empty(16, 8, 8, 1280, device=DEV)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.conv3x3(x, w, out)                 # the eager warm-up creates the workspaces outside the capture
+        eager = out.clone()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ops.conv3x3(x, w, out)
+        ops.conv3x3(x, w, out)
+    for _ in range(3):
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, eager)
+    assert _splitk_flags_clear()
+    with ops.launch_options(split_k=1):
+        whole = torch.empty_like(out)
+        ops.conv3x3(x, w, whole)
+    assert not torch.equal(whole, eager) and _rel(whole, eager) < 5e-5     # the captured launches did split

@@ -209,10 +209,15 @@ def test_get_learned_conditioning_end_to_end(gold, models):
     assert err < TOL
     iB, iN = extra["placeholder2indices"]["z"]
     assert torch.equal(iB.cpu(), g["indices_B"]) and torch.equal(iN.cpu(), g["indices_N"])
-    # de-duplicated encode (one of the 16 identical layer copies) == full 16x encode, bit for bit
-    fr.dedup_layer_copies = False
-    c_full, _, _ = ldm.get_learned_conditioning(tokens, None, face)
-    assert torch.equal(c, c_full)
+    # de-duplicated encode (one of the 16 identical layer copies) == full 16x encode: bit for bit with the whole-tile
+    # GEMM schedule; the split-K schedule depends on the row count, which re-associates the K sums
+    from adaprompt_b200 import ops
+    with ops.launch_options(split_k=1):
+        c_dedup, _, _ = ldm.get_learned_conditioning(tokens, None, face)
+        fr.dedup_layer_copies = False
+        c_full, _, _ = ldm.get_learned_conditioning(tokens, None, face)
+    assert torch.equal(c_dedup, c_full)
+    assert _rel(c, c_full) < TOL          # different bf16 rounding flips through 12 layers, same accuracy class
     # config #2 of BASELINE.json: batch 32 identities -> 16 ID tokens each, spliced into 32 prompts
     face32 = torch.nn.functional.normalize(torch.randn(32, 512, generator=torch.Generator().manual_seed(11)), dim=-1).cuda()
     tokens32 = torch.tensor([to.subject_prompt_ids(77)] * 32).cuda()
