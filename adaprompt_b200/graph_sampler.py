@@ -70,6 +70,9 @@ class _StepGraph:
         self.extra_info = dict(extra_info) if extra_info is not None else None
         prompts = list(c_in_c) + (list(uncond[1]) if cfg_on else [])
         self.c2 = (self.ctx, prompts, self.extra_info)
+        # time-embedding rows of every step (model.time_embedding_rows): filled per run(), indexed in the graph
+        self.emb_table = None
+        self.emb_rows = None
         self.graph = None
         self.kvs = None
         self.kernels = 0
@@ -87,11 +90,26 @@ class _StepGraph:
                 self.graph = None  # the model re-allocated its K / V^T buffers: the captured pointers are stale
             self.kvs = kvs
 
+    def load_time_embedding(self, t_values: torch.Tensor):
+        """emb_layers(time_embed(t)) of all steps in one pass (t alone decides them); the graph picks the row of its step."""
+        fn = getattr(self._sampler.model, "time_embedding_rows", None)
+        if fn is None or self.extra_info is None:
+            return
+        rows = fn(t_values)
+        if self.emb_table is None or self.emb_table.shape[1] != rows.shape[1]:
+            self.emb_table = torch.zeros(self.max_steps, rows.shape[1], dtype=torch.float32, device=rows.device)
+            self.emb_rows = torch.zeros(self.x_in.shape[0], rows.shape[1], dtype=torch.float32, device=rows.device)
+            self.extra_info["emb_rows"] = self.emb_rows
+            self.graph = None
+        self.emb_table[: rows.shape[0]].copy_(rows)
+
     def body(self, num_steps_tensorless):
         b = self.b
         self.x_in[:b].copy_(self.x)
         if self.cfg_on:
             self.x_in[b:].copy_(self.x)
+        if self.emb_rows is not None:      # all samples of a step share its timestep (ddim.py:222: ts = full((b,), step))
+            torch.index_select(self.emb_table, 0, self.step_idx.long().repeat(self.emb_rows.shape[0]), out=self.emb_rows)
         eps = self._sampler.model.apply_model(self.x_in, self.t_buf, self.c2)
         ops.cfg_ddim_update(self.x, eps, self.coef_table, self.x, self.pred, has_uncond=self.cfg_on, noise=self.noise,
                             step_idx=self.step_idx)
@@ -154,6 +172,7 @@ def run(sampler, img, cond, uncond, steps, scales, temperature, log_every_t, int
                     cache.pop(next(iter(cache)))
         st.coef_table[:total].copy_(coef_host, non_blocking=True)
         st.t_table[:total].copy_(t_host, non_blocking=True)
+        st.load_time_embedding(st.t_table[:total])
         st.load_conditioning(cond, uncond)
         if st.graph is not None and st.pack_epoch != PackedModule.PACK_EPOCH:
             st.graph = None     # some module repacked its weights since the capture: the graph holds stale pointers

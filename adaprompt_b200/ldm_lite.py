@@ -129,6 +129,12 @@ class LatentDiffusionLite(nn.Module):
         iter_type = (extra_info or {}).get("iter_type", "normal_recon")
         return self.model.diffusion_model.context_kv(c_static_emb, batch, iter_type)
 
+    def time_embedding_rows(self, timesteps: torch.Tensor):
+        """Hook for the CUDA-graph sampler: every ResBlock's emb_layers(time_embed(t)) for a vector of timesteps, [len(t),
+        sum Cout] - the part of the UNet forward that depends on t alone, hoisted out of the 50-step loop (the sampler
+        hands the row of the current step back through extra_info['emb_rows'])."""
+        return self.model.diffusion_model.time_embedding(timesteps)[1]
+
     def apply_model(self, x_noisy, t, cond, return_ids=False):
         """ddpm.py:2192-2201,2292."""
         if not isinstance(cond, dict):

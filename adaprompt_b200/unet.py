@@ -602,7 +602,7 @@ class UNetModel(PackedModule):
                                                        ca_layer_indices=distill_layer_indices)
         acts = {}
         try:
-            out = self._forward_nhwc(x, timesteps, kvs, img_mask, distill_layer_indices, acts)
+            out = self._forward_nhwc(x, timesteps, kvs, img_mask, distill_layer_indices, acts, ei.get("emb_rows", None))
         finally:
             if distill_old is not None:
                 self.set_cross_attn_flags(ca_flag_dict=distill_old, ca_layer_indices=distill_layer_indices)
@@ -613,9 +613,16 @@ class UNetModel(PackedModule):
                                                for key in ("outfeat", "attn", "attnscore", "q")}      # :1031-1035
         return out
 
-    def _forward_nhwc(self, x, timesteps, kvs, img_mask, capture_layers=(), acts=None):
+    def _forward_nhwc(self, x, timesteps, kvs, img_mask, capture_layers=(), acts=None, emb_rows=None):
         pk = self.packed()
-        _, rows = self.time_embedding(timesteps)
+        if emb_rows is not None:
+            # precomputed by the caller from the SAME timesteps (graph_sampler: one table per sample() call, the 113 MB of
+            # fp32 emb_layers weights are read once instead of once per step); bit-identical to computing them here
+            if emb_rows.shape != (x.shape[0], pk["emb_total"]) or emb_rows.dtype != torch.float32:
+                raise ValueError("extra_info['emb_rows'] must be fp32 [batch, sum of ResBlock channels]")
+            rows = emb_rows
+        else:
+            _, rows = self.time_embedding(timesteps)
         offs = pk["emb_offs"]
 
         def emb_rows_of(rb):
