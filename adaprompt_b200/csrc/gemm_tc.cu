@@ -866,10 +866,24 @@ static int make_epilogue_maps(GemmParams& p, int out_cols, bool conv) {
   return rc;
 }
 
-static int pick_bn(int N, int geglu, int bn_hint) {
+// N-tile width.  160 divides every channel count of the UNet (320 .. 2560) without padding and is the default for
+// those; the 256-wide tile (the most efficient tcgen05 shape: one A tile feeds 256 output columns) wins once the K loop
+// dominates the tile - measured with scripts/bench_bn.py on B200 (profiles/r02_splitk.md): linear GEMMs without a
+// residual and N >= 1280 from K = 640, everything from K = 2560 (with an fp32 residual the 160-wide tile has three
+// epilogue slots against one at 256, so short-K GEMMs with a residual stay at 160), convolutions
+// to 1280 channels from 32 row tiles (16x16 x 16 samples); the 160 remainder tiles of those are what split-K is for.
+static int pick_bn(int N, int geglu, int bn_hint, int K, bool residual, bool conv, int m_tiles) {
   if (geglu) return 256;
   if (bn_hint == 64 || bn_hint == 128 || bn_hint == 160 || bn_hint == 256) return bn_hint;
-  if (N % 160 == 0) return 160;
+  if (N % 160 == 0) {
+#ifdef AF_BN160_ONLY   // A/B builds (scripts/build_alt.sh): the round-1 rule
+    return 160;
+#endif
+    if (conv) return (N % 256 == 0 && N >= 1024 && m_tiles >= 32) ? 256 : 160;
+    if (K >= 2560) return 256;
+    if (!residual && N >= 1280 && K >= 640) return 256;
+    return 160;
+  }
   if (N % 256 == 0) return 256;
   if (N % 128 == 0) return 128;
   if (N <= 64) return 64;
@@ -925,7 +939,7 @@ extern "C" int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* 
   memset(&p, 0, sizeof(p));
   p.trace = ep->trace;
   const int K = K0 + K1;
-  const int bn = pick_bn(N, ep->geglu, bn_hint);
+  const int bn = pick_bn(N, ep->geglu, bn_hint, K, ep->residual != nullptr, false, (M + 127) / 128);
   const bool pair = want_pair(ep->pair_mode, (M + 127) / 128, (N + bn - 1) / bn, bn, 0);
   AF_CHECK_ARG(!ep->geglu || N % 256 == 0, "geglu: packed N=%d must be a multiple of 256", N);
   {
@@ -998,9 +1012,10 @@ extern "C" int af_conv3x3_bf16(const void* X0, int C0, const void* X1, int C1, c
   p.trace = ep->trace;
   const int Cin = C0 + C1;
   const int Ho = stride == 1 ? H : H / 2, Wo = stride == 1 ? W : W / 2;
-  const int bn = pick_bn(Cout, 0, bn_hint);
   int bw, bh, nb;
   conv_tile_box(Ho, Wo, &bw, &bh, &nb);
+  const int bn = pick_bn(Cout, 0, bn_hint, 9 * Cin, ep->residual != nullptr, true,
+                         ((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * ((B + nb - 1) / nb));
   const bool pair = want_pair(ep->pair_mode, ((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * ((B + nb - 1) / nb), (Cout + bn - 1) / bn, bn, 1);
   p.bw = bw; p.bh = bh; p.nb = nb;
   p.tiles_w = (Wo + bw - 1) / bw;
