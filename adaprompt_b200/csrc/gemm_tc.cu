@@ -112,7 +112,7 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // GELU for the GEGLU epilogue: x * Phi(x) in its tanh form, 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))), one MUFU
 // op per element.  |tanh form - erf form| <= 4.8e-4 absolute (rel-L2 2e-4 for unit-variance gates), an order of
 // magnitude below the bf16 rounding of the product this epilogue writes (rel-L2 1.7e-3); the erf form cost 3x the
-// instructions and left the tensor pipe idle 85 % of the time (profiles/r01_gemm_geglu_before.md).
+// instructions and left the tensor pipe idle 85 % of the time (ncu --set full of the erf-form epilogue, round 1; the capture was not kept).
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float x2 = x * x;
   const float u = x * fmaf(0.0356774081f, x2, 0.7978845608f);

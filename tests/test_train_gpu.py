@@ -329,7 +329,8 @@ def test_unet_context_gradient_matches_oracle_autograd():
     err = _rel(c.grad, c_ref.grad)
     per_layer = [_rel(c.grad.reshape(B, 16, 77, 768)[:, l], c_ref.grad.reshape(B, 16, 77, 768)[:, l]) for l in range(16)]
     print("context grad rel-L2", err, "per layer", [f"{e:.3f}" for e in per_layer])
-    assert err < 5e-2, (err, per_layer)
+    # measured on B200: 9.2e-3 overall, 8e-3 .. 2.9e-2 per layer (bf16 operands through 25 blocks of backward): 2x that
+    assert err < 2e-2 and max(per_layer) < 6e-2, (err, per_layer)
 
 
 # ------------------------------------------------------------------------------------------------ conditioning half
@@ -361,7 +362,7 @@ def _cond_reference(sd_sbg, sd_frozen, hw, id_embs, tokens):
     return to.frozen_clip_encode(sd_frozen, tokens, static)
 
 
-def _compare_param_grads(module, sd_ref, prefix="", tol=5e-2, skip=()):
+def _compare_param_grads(module, sd_ref, prefix="", tol=3e-2, skip=()):     # measured worst 1.3e-2 .. 1.5e-2
     worst = ("", 0.0)
     for name, p in module.named_parameters():
         ref = sd_ref[prefix + name].grad
@@ -410,7 +411,7 @@ def test_conditioning_gradients_match_oracle_autograd(kv_mult):
     assert _rel(tok_g[rows.cuda()], tok_ref[rows]) < 5e-2 and float(tok_g.abs().sum()) > 0
     e_hw = _rel(sbg.hidden_state_layer_weights.grad, 5 * hw_ref.grad)       # grad scaler 5 (subj_basis_generator.py:580)
     print("worst parameter", worst, "hidden_state_layer_weights", e_hw)
-    assert e_hw < 5e-2
+    assert e_hw < 4e-2                                                       # measured 1.2e-2 .. 1.8e-2
     assert all(p.grad is None for p in frozen.parameters())
 
 
@@ -462,7 +463,7 @@ def test_distill_step_end_to_end_gradients():
         e = _rel(p.grad / scale, ref)
         worst = max(worst, (name, e), key=lambda t: t[1])
     print("end-to-end worst parameter gradient error", worst, "n trainable", len(trainable_parameters(sbg)))
-    assert worst[1] < 8e-2, worst
+    assert worst[1] < 3e-2, worst                                            # measured 1.5e-2
 
 
 def test_stage1_trainer_graph_matches_eager_and_steps_the_optimizer():
