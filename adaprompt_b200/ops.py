@@ -79,22 +79,31 @@ _splitk_ws = {}
 
 
 def _splitk_workspace(device) -> Optional[torch.Tensor]:
-    """Split-K workspace (af_epilogue.splitk_ws).  Eager launches: one per (device, stream), because two GEMMs that run
-    concurrently must not share flags.  Launches recorded into a CUDA graph: one per device, shared by all captured
-    graphs (replays are stream-ordered; two graphs of one device must not replay concurrently).  Zeroed once - the
-    kernel leaves the flag region zero.  Nothing is allocated while a capture is in progress: the eager warm-up that
-    precedes every capture creates both; without a workspace the whole-tile schedule runs."""
+    """Split-K workspace (af_epilogue.splitk_ws), or None for the whole-tile schedule.
+
+    A split tile's finisher block spins until the blocks holding the other K ranges of the tile have run, which is only
+    safe while the kernel's blocks are not kept off the SMs by ANOTHER kernel that is itself waiting the same way.  So
+    per device the schedule is enabled for ONE eager stream at a time (it moves to another stream only once everything
+    submitted to the previous one has completed - every path of this package is single-stream) and for launches recorded
+    into CUDA graphs (replays are stream-ordered; graphs of one device must not replay concurrently with each other or
+    with eager GEMMs); a GEMM on any other stream gets the whole-tile schedule.  Each of the two has its own workspace,
+    zeroed once - the kernel leaves the flag region zero.  Nothing is allocated while a capture is in progress: the
+    eager warm-up that precedes every capture creates both."""
     capturing = torch.cuda.is_current_stream_capturing()
-    gkey = (device.index, "graph")
+    st = _splitk_ws.get(device.index)
     if capturing:
-        return _splitk_ws.get(gkey)
-    if gkey not in _splitk_ws:
-        _splitk_ws[gkey] = torch.zeros(SPLITK_WS_BYTES // 4, dtype=torch.float32, device=device)
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    ws = _splitk_ws.get(key)
-    if ws is None:
-        ws = _splitk_ws[key] = torch.zeros(SPLITK_WS_BYTES // 4, dtype=torch.float32, device=device)
-    return ws
+        return st["graph"] if st is not None else None
+    cur = torch.cuda.current_stream(device)
+    if st is None:
+        st = _splitk_ws[device.index] = {
+            "stream": cur,
+            "eager": torch.zeros(SPLITK_WS_BYTES // 4, dtype=torch.float32, device=device),
+            "graph": torch.zeros(SPLITK_WS_BYTES // 4, dtype=torch.float32, device=device)}
+    if st["stream"].cuda_stream != cur.cuda_stream:
+        if not st["stream"].query():
+            return None
+        st["stream"] = cur
+    return st["eager"]
 
 
 class _LaunchOptions:

@@ -71,8 +71,10 @@ typedef struct af_epilogue {
   void* splitk_ws;        /* NULL (whole-tile schedule only), or a caller-owned device workspace whose first
                              AF_SPLITK_FLAG_BYTES are ZERO when the call is issued (the kernel leaves them zero again):
                              the tiles of the last, partial wave are cut into K ranges on different SMs, the partial fp32
-                             accumulators travel through this buffer and are added in K order (bit-reproducible).  One
-                             workspace per stream: two GEMMs running concurrently must not share it. */
+                             accumulators travel through this buffer and are added in K order (bit-reproducible).  The
+                             block that adds them waits for the blocks holding the other ranges: launches that pass a
+                             workspace must not run CONCURRENTLY with each other on one device (stream-ordered use only;
+                             concurrent GEMMs pass NULL), and never share a workspace across streams. */
   long long splitk_ws_bytes; /* size of splitk_ws; bounds the number of partial tiles (128 x BN fp32 each) */
   int split_k;            /* 0 = auto (cost model), 1 = never, n > 1 = cut every remainder tile into n K ranges (tests) */
 } af_epilogue;

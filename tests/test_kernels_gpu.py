@@ -563,7 +563,8 @@ def test_conv_and_geglu_pair_mode_match_single_cta():
 def _splitk_flags_clear():
     from adaprompt_b200 import ops
     torch.cuda.synchronize()
-    return all(int(ws[:4096].view(torch.int32).abs().sum().item()) == 0 for ws in ops._splitk_ws.values())
+    return all(int(st[k][:4096].view(torch.int32).abs().sum().item()) == 0
+               for st in ops._splitk_ws.values() for k in ("eager", "graph"))
 
 
 @pytest.mark.parametrize("M,N,K,bn,res,bf16out,split", [
@@ -639,9 +640,14 @@ def test_split_k_replays_from_a_cuda_graph():
     out = torch.empty(16, 8, 8, 1280, device=DEV)
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        ops.conv3x3(x, w, out)                 # the eager warm-up creates the workspaces outside the capture
-        eager = out.clone()
+    ops.conv3x3(x, w, out)                     # an eager launch creates the workspaces outside the capture
+    eager = out.clone()
+    big = torch.empty(1 << 28, device=DEV)
+    for _ in range(4):
+        big.normal_()                          # keeps the first stream busy for a few milliseconds
+    with torch.cuda.stream(side):              # a second eager stream gets the whole-tile schedule while the first has
+        side_out = torch.empty_like(out)       # work in flight (see ops._splitk_workspace)
+        ops.conv3x3(x, w, side_out)
     torch.cuda.current_stream().wait_stream(side)
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
@@ -657,3 +663,4 @@ def test_split_k_replays_from_a_cuda_graph():
         whole = torch.empty_like(out)
         ops.conv3x3(x, w, whole)
     assert not torch.equal(whole, eager) and _rel(whole, eager) < 5e-5     # the captured launches did split
+    assert torch.equal(side_out, whole)
