@@ -26,7 +26,33 @@ def shard_conditioning(cond, n_images: int, world_size: int, rank: int, layers: 
     if c.shape[0] != n_images * layers:
         raise ValueError(f"context has {c.shape[0]} rows, expected {n_images}*{layers}")
     b, e = shard_range(n_images, world_size, rank)
-    return (c[b * layers:e * layers], list(prompts[b:e]), dict(extra) if extra is not None else None)
+    return (c[b * layers:e * layers], list(prompts[b:e]), _shard_extra(extra, n_images, b, e))
+
+
+def _shard_extra(extra, n_images: int, b: int, e: int):
+    """Per-image entries of extra_info follow the shard: tensors whose leading dimension is the global batch (img_mask
+    [B,1,H,W], prompt_emb_mask [B,77,1], ...) are sliced, the placeholder index pairs (indices_B, indices_N) of
+    `placeholder2indices` (embedding_manager.py:1292-1330) keep the entries of this rank's images, re-based to the local
+    batch; scalars and flags are shared."""
+    if extra is None:
+        return None
+    out = {}
+    for k, v in extra.items():
+        if torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == n_images:
+            out[k] = v[b:e]
+        elif k == "placeholder2indices" and isinstance(v, dict):
+            local = {}
+            for name, pair in v.items():
+                if pair is None:
+                    local[name] = None
+                    continue
+                iB, iN = pair
+                keep = (iB >= b) & (iB < e)
+                local[name] = (iB[keep] - b, iN[keep])
+            out[k] = local
+        else:
+            out[k] = v
+    return out
 
 
 def sample_sharded(sampler, S: int, n_images: int, shape: Sequence[int], conditioning, unconditional_conditioning,

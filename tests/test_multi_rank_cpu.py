@@ -53,6 +53,34 @@ def test_shard_range_partitions_exactly():
             assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
 
 
+def test_shard_conditioning_slices_per_image_entries_of_extra_info():
+    """img_mask / prompt_emb_mask rows and the placeholder index pairs follow the rank's images (they were
+    shared unsliced); the union over the ranks is the global conditioning."""
+    import torch
+    from adaprompt_b200.parallel_sampling import shard_conditioning, shard_range
+    n, layers = 5, 16
+    c = torch.arange(n * layers * 2 * 3, dtype=torch.float32).reshape(n * layers, 2, 3)
+    iB = torch.tensor([0, 0, 2, 2, 3, 4, 4])
+    iN = torch.tensor([5, 6, 5, 6, 9, 5, 6])
+    extra = {"use_layerwise_context": True, "img_mask": torch.arange(n * 4.).reshape(n, 1, 2, 2),
+             "prompt_emb_mask": torch.ones(n, 77, 1), "placeholder2indices": {"z": (iB, iN), "y": None},
+             "use_conv_attn_kernel_size": -1}
+    seen_rows, seen_pairs = [], []
+    for rank in range(2):
+        b, e = shard_range(n, 2, rank)
+        cc, prompts, ex = shard_conditioning((c, [f"p{i}" for i in range(n)], extra), n, 2, rank)
+        assert cc.shape[0] == (e - b) * layers and prompts == [f"p{i}" for i in range(b, e)]
+        assert torch.equal(ex["img_mask"], extra["img_mask"][b:e]) and ex["prompt_emb_mask"].shape[0] == e - b
+        lb, ln = ex["placeholder2indices"]["z"]
+        assert ex["placeholder2indices"]["y"] is None and bool((lb >= 0).all()) and bool((lb < e - b).all())
+        seen_pairs += [(int(x) + b, int(y)) for x, y in zip(lb, ln)]
+        seen_rows.append(cc)
+        assert ex["use_layerwise_context"] is True and ex["use_conv_attn_kernel_size"] == -1
+    assert torch.equal(torch.cat(seen_rows), c)
+    assert seen_pairs == list(zip(iB.tolist(), iN.tolist()))
+    assert extra["placeholder2indices"]["z"][0] is iB            # the caller's dict is untouched
+
+
 def test_world2_gloo_sharded_sampling_matches_single_process(tmp_path):
     n_images, world = 5, 2
     port = _free_port()
