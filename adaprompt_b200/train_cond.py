@@ -217,13 +217,16 @@ def sbg_forward_train(sbg, arc2face_id_embs: torch.Tensor, out_id_embs_scale: fl
 
 def conditioning_train(frozen_tm: CLIPTextTransformer, tokens: torch.Tensor, adaface_subj_embs: torch.Tensor,
                        placeholder_token: int, K: int = 16, dedup: bool = True,
-                       layers_identical: Optional[bool] = None) -> torch.Tensor:
+                       layers_identical: Optional[bool] = None, groups: int = 1) -> torch.Tensor:
     """EmbeddingManager.forward + FrozenCLIPEmbedder with grad w.r.t. adaface_subj_embs [BS, 16, K, 768].
     tokens int64 [B, 77] -> c fp32 [16*B, 77, 768] (layer index minor to batch, embedding_manager.py:1349-1353).
     dedup: encode one of the 16 layer copies when they are identical (always true for the face branch, :558);
     layers_identical: what the caller knows about that by construction (None: compare on the device - one host read).
     No host synchronisation otherwise: the i-th prompt that holds the placeholder takes subject i mod BS (the
-    reference's repeat to the number of occurrences, :1449-1451), prompts without it pass through the splice."""
+    reference's repeat to the number of occurrences, :1449-1451), prompts without it pass through the splice.
+    groups: the rows are `groups` independent forward calls stacked along the batch (the micro-batches of an optimizer
+    step): occurrences are counted, and subjects assigned, within each group of B / groups prompts and BS / groups
+    subjects - exactly what `groups` separate calls would do."""
     B, N = tokens.shape
     L = N_CA_LAYERS
     tw = frozen_tm.embeddings.token_embedding.weight.detach().float().contiguous()
@@ -240,19 +243,28 @@ def conditioning_train(frozen_tm: CLIPTextTransformer, tokens: torch.Tensor, ada
         else:
             identical = bool(layers_identical)
     w = frozen_tm.last_layers_skip_weights
+    if B % groups or BS % groups:
+        raise ValueError("conditioning_train: batch / subjects not divisible into `groups` calls")
+
+    def occurrence_index(has_rows: torch.Tensor, n_src: int) -> torch.Tensor:
+        """row -> index of the subject it takes: the i-th occurrence inside its group takes the group's subject i mod n."""
+        hg = has_rows.view(groups, -1).int()
+        rank = (torch.cumsum(hg, 1) - 1).clamp_min(0)
+        per = n_src // groups
+        base = torch.arange(groups, device=has_rows.device, dtype=rank.dtype)[:, None] * per
+        return (rank % per + base).reshape(-1).to(torch.int32).contiguous()
+
     if identical:
-        rank = (torch.cumsum(has.int(), 0) - 1).clamp_min(0).to(torch.int32)
         src = adaface_subj_embs[:, 0, :K].contiguous()                                             # [BS, K, 768]
-        src_index = (rank % BS).contiguous()
+        src_index = occurrence_index(has, BS)
         spliced = SpliceRowsFn.apply(emb, src, first_b, src_index)
         z = clip_encode_train(frozen_tm, spliced + pos[None, :N], w, trainable=False)
         return z.unsqueeze(1).expand(B, L, N, z.shape[-1]).reshape(B * L, N, z.shape[-1])
     emb16 = emb.unsqueeze(1).repeat(1, L, 1, 1).view(B * L, N, -1)
     first16 = first_b.repeat_interleave(L).contiguous()
     has16 = first16 >= 0
-    rank16 = (torch.cumsum(has16.int(), 0) - 1).clamp_min(0).to(torch.int32)
     src = adaface_subj_embs.reshape(BS * adaface_subj_embs.shape[1], *adaface_subj_embs.shape[2:])[:, :K].contiguous()
-    src_index = (rank16 % src.shape[0]).contiguous()
+    src_index = occurrence_index(has16, src.shape[0])
     spliced = SpliceRowsFn.apply(emb16, src, first16, src_index)
     return clip_encode_train(frozen_tm, spliced + pos[None, :N], w, trainable=False)
 
@@ -385,11 +397,13 @@ class DistillStep:
         a = self._acp(x0.device)[t].view(-1, 1, 1, 1)
         return a.sqrt() * x0 + (1 - a).sqrt() * noise
 
-    def context(self, face_embs: torch.Tensor, tokens: torch.Tensor) -> torch.Tensor:
+    def context(self, face_embs: torch.Tensor, tokens: torch.Tensor, groups: int = 1) -> torch.Tensor:
+        """groups > 1: the rows are that many micro-batches stacked along the batch (GraphedAccumStep)."""
         with torch.no_grad():
             _, id_embs = arc2face_forward_face_embs(self.tokenizer, self.arc2face, face_embs)     # embedding_manager.py:1424
         subj, _ = sbg_forward_train(self.sbg, id_embs)       # 16 identical layer copies by construction (:558)
-        return conditioning_train(self.frozen_tm, tokens, subj, self.placeholder_token, layers_identical=True)
+        return conditioning_train(self.frozen_tm, tokens, subj, self.placeholder_token, layers_identical=True,
+                                  groups=groups)
 
     @torch.no_grad()
     def teacher_eps(self, x0, t, noise, face_embs) -> torch.Tensor:
@@ -476,14 +490,20 @@ class DistillStep:
         return float(loss.detach())
 
 
-class GraphedMicroStep:
-    """One WHOLE micro-batch of DistillStep replayed from one CUDA graph: Arc2Face prompt, SubjBasisGenerator and frozen
-    CLIP forward, UNet forward + backward, conditioning backward with every parameter gradient accumulated in place into
-    its GradBucket view.  The conditioning half is ~2000 small launches per micro-batch whose host issue time (22 ms)
-    was twice their device time; nothing on the path reads back to the host (no .item(), no nonzero, token ids cached
-    on the device), so the only per-replay host work is copying the batch into the static buffers.
-    Recaptured when the geometry, the parameter storage (Prodigy re-binds parameters into its bucket at its first
-    step) or a weight pack of a frozen module changes."""
+class GraphedAccumStep:
+    """ALL micro-batches of one optimizer step of DistillStep replayed from one CUDA graph.
+
+    * The conditioning (Arc2Face prompt, SubjBasisGenerator, frozen CLIP) depends on the identities and prompts only,
+      not on the UNet: it runs ONCE on the concatenation of the micro-batches (its GEMMs have 77 rows per sample and are
+      latency-bound, so 8 samples cost what 4 do), the UNet forward + backward runs per micro-batch on its slice of the
+      context, and the conditioning backward runs once on the concatenated context gradients.  The parameter gradients
+      are the same sums the per-micro-batch loop accumulates (embedding_manager / ddpm.py:595-633 with
+      accumulate_grad_batches), up to fp32 summation order.
+    * Every parameter gradient is accumulated in place into its GradBucket view; nothing on the path reads back to the
+      host (no .item(), no nonzero, token ids and the schedule resident on the device), so the only per-replay host
+      work is copying the batches into the static buffers.
+    Recaptured when the geometry, the parameter storage (Prodigy re-binds parameters into its bucket at its first step)
+    or a weight pack of a frozen module changes."""
 
     KEYS = ("x0", "t", "noise", "face_embs", "tokens", "teacher_eps")
 
@@ -491,23 +511,35 @@ class GraphedMicroStep:
         self.step, self.bucket, self.accum = step, bucket, accum
         self._g = {}
 
-    def _key(self, batch):
+    def _key(self, batches):
         from .attention import PackedModule
         ps = self.bucket.params
-        return (tuple((tuple(batch[k].shape), batch[k].dtype) for k in self.KEYS), ps[0].data_ptr(), ps[-1].data_ptr(),
-                PackedModule.PACK_EPOCH)
+        return (tuple((tuple(b[k].shape), b[k].dtype) for b in batches for k in self.KEYS), ps[0].data_ptr(),
+                ps[-1].data_ptr(), PackedModule.PACK_EPOCH)
 
-    def _build(self, batch):
-        st = {k: batch[k].clone() for k in self.KEYS}
+    def _build(self, batches):
+        st = {"in": [{k: b[k].clone() for k in self.KEYS} for b in batches]}
+        step, n = self.step, len(batches)
 
         def run():
-            loss = self.step.loss(st["x0"], st["t"], st["noise"], st["teacher_eps"], st["face_embs"], st["tokens"])
-            (loss / self.accum).backward()
-            return loss.detach()
+            ins = st["in"]
+            c = step.context(torch.cat([i["face_embs"] for i in ins]), torch.cat([i["tokens"] for i in ins]), groups=n)
+            rows = c.shape[0] // n                                  # (b l) order: a micro-batch owns a contiguous row range
+            losses, grads = [], []
+            for k, i in enumerate(ins):
+                ck = c.detach()[k * rows:(k + 1) * rows].clone().requires_grad_(True)
+                eps = unet_forward_train(step.unet, step.q_sample(i["x0"], i["t"], i["noise"]), i["t"], ck,
+                                         dict(step.extra_info))
+                loss = distill_loss(eps, i["teacher_eps"])
+                (g,) = torch.autograd.grad(loss, ck)
+                losses.append(loss.detach())
+                grads.append(g)
+            c.backward(torch.cat(grads) * (1.0 / self.accum))
+            return torch.stack(losses)
 
         for p, v in zip(self.bucket.params, self.bucket.views):
             p.grad = v                                  # AccumulateGrad then adds in place (captured as kernels)
-        keep = self.bucket.flat.clone()                 # gradients of earlier micro-batches of this optimizer step
+        keep = self.bucket.flat.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -516,30 +548,32 @@ class GraphedMicroStep:
         torch.cuda.current_stream().wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            st["loss"] = run()
+            st["losses"] = run()
         self.bucket.flat.copy_(keep)
         st["graph"] = graph
         return st
 
-    def __call__(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
-        key = self._key(batch)
+    def __call__(self, batches: Sequence[Dict[str, torch.Tensor]]) -> torch.Tensor:
+        """-> the micro-batch losses [accum] (detached); the gradients of sum_i loss_i / accum are added to the bucket."""
+        key = self._key(batches)
         st = self._g.get(key)
         if st is None:
             self._g.clear()                             # one live geometry: a stale capture holds GBs of activations
-            st = self._g[key] = self._build(batch)
-        for k in self.KEYS:
-            st[k].copy_(batch[k])
+            st = self._g[key] = self._build(batches)
+        for dst, b in zip(st["in"], batches):
+            for k in self.KEYS:
+                dst[k].copy_(b[k])
         st["graph"].replay()
-        return st["loss"].clone()
+        return st["losses"].clone()
 
 
 class Stage1Trainer:
     """One optimizer step of the Stage-1 distillation (training_step ddpm.py:595-633 around guided_denoise :2483-2532):
     `accum` micro-batches -> gradients accumulate in the flat bucket -> one all-reduce (mean over ranks) -> clip by norm
     0.5 -> Prodigy (ldm/prodigy.py) on the same bucket.
-    use_graph: "step" (default) - each micro-batch is ONE CUDA graph (GraphedMicroStep); True - only the frozen UNet's
-    forward + backward-to-context is a graph (train.GraphedUNetLoss), the conditioning runs on the eager tape;
-    False - everything eager."""
+    use_graph: "step" (default) - the micro-batches of an optimizer step are ONE CUDA graph with the conditioning
+    batched across them (GraphedAccumStep); True - only the frozen UNet's forward + backward-to-context is a graph
+    (train.GraphedUNetLoss), the conditioning runs per micro-batch on the eager tape; False - everything eager."""
 
     def __init__(self, step: "DistillStep", params: Sequence[torch.nn.Parameter], world_size: int = 1, group=None,
                  accum: int = 2, max_grad_norm: float = 0.5, optimizer=None, use_graph="step"):
@@ -549,25 +583,25 @@ class Stage1Trainer:
         self.bucket = GradBucket(params)
         self.optimizer = optimizer if optimizer is not None else Prodigy(self.bucket.params)
         self.use_graph = use_graph
-        self._gstep = GraphedMicroStep(step, self.bucket, accum) if use_graph == "step" else None
+        self._gstep = GraphedAccumStep(step, self.bucket, accum) if use_graph == "step" else None
         self.allreduce_ms = None
-
-    def _micro(self, b: Dict[str, torch.Tensor]) -> torch.Tensor:
-        if self._gstep is None:
-            return self.step.micro_backward(b, accum=self.accum, use_graph=bool(self.use_graph))
-        if b.get("teacher_eps") is None:            # the teacher (no grad) runs outside the captured micro-step
-            b = dict(b, teacher_eps=self.step.teacher_eps(b["x0"], b["t"], b["noise"], b["face_embs"]))
-        return self._gstep(b)
 
     def optimizer_step(self, batches: Sequence[Dict[str, torch.Tensor]], time_allreduce: bool = False):
         """-> {"loss": 0-d tensor (mean over the micro-batches), "grad_norm": 0-d tensor (before clipping)}."""
         if len(batches) != self.accum:
             raise ValueError(f"expected {self.accum} micro-batches, got {len(batches)}")
         self.bucket.begin_step()
-        loss_sum = None
-        for b in batches:
-            li = self._micro(b)
-            loss_sum = li if loss_sum is None else loss_sum + li
+        if self._gstep is not None:
+            # the teacher (no grad) runs outside the captured step
+            batches = [b if b.get("teacher_eps") is not None else
+                       dict(b, teacher_eps=self.step.teacher_eps(b["x0"], b["t"], b["noise"], b["face_embs"]))
+                       for b in batches]
+            loss_sum = self._gstep(batches).sum()
+        else:
+            loss_sum = None
+            for b in batches:
+                li = self.step.micro_backward(b, accum=self.accum, use_graph=bool(self.use_graph))
+                loss_sum = li if loss_sum is None else loss_sum + li
         if time_allreduce and self.world_size > 1:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
