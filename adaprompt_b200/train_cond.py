@@ -498,7 +498,8 @@ class GraphedAccumStep:
       latency-bound, so 8 samples cost what 4 do), the UNet forward + backward runs per micro-batch on its slice of the
       context, and the conditioning backward runs once on the concatenated context gradients.  The parameter gradients
       are the same sums the per-micro-batch loop accumulates (embedding_manager / ddpm.py:595-633 with
-      accumulate_grad_batches), up to fp32 summation order.
+      accumulate_grad_batches), up to fp32 summation order.  With fuse_unet (default) the frozen UNet also runs once,
+      on all micro-batches as one batch (same gradient of sum_k MSE_k / accum).
     * Every parameter gradient is accumulated in place into its GradBucket view; nothing on the path reads back to the
       host (no .item(), no nonzero, token ids and the schedule resident on the device), so the only per-replay host
       work is copying the batches into the static buffers.
@@ -507,15 +508,15 @@ class GraphedAccumStep:
 
     KEYS = ("x0", "t", "noise", "face_embs", "tokens", "teacher_eps")
 
-    def __init__(self, step: "DistillStep", bucket: GradBucket, accum: int):
-        self.step, self.bucket, self.accum = step, bucket, accum
+    def __init__(self, step: "DistillStep", bucket: GradBucket, accum: int, fuse_unet: bool = True):
+        self.step, self.bucket, self.accum, self.fuse_unet = step, bucket, accum, fuse_unet
         self._g = {}
 
     def _key(self, batches):
         from .attention import PackedModule
         ps = self.bucket.params
         return (tuple((tuple(b[k].shape), b[k].dtype) for b in batches for k in self.KEYS), ps[0].data_ptr(),
-                ps[-1].data_ptr(), PackedModule.PACK_EPOCH)
+                ps[-1].data_ptr(), PackedModule.PACK_EPOCH, self.fuse_unet)
 
     def _build(self, batches):
         st = {"in": [{k: b[k].clone() for k in self.KEYS} for b in batches]}
@@ -526,6 +527,19 @@ class GraphedAccumStep:
             c = step.context(torch.cat([i["face_embs"] for i in ins]), torch.cat([i["tokens"] for i in ins]), groups=n)
             rows = c.shape[0] // n                                  # (b l) order: a micro-batch owns a contiguous row range
             losses, grads = [], []
+            same = all(i["x0"].shape == ins[0]["x0"].shape for i in ins)
+            if self.fuse_unet and same:
+                # The frozen UNet sees the micro-batches as ONE batch (the accumulation loop exists for the memory of
+                # smaller GPUs; 180 GB hold the activations of all of them, and the kernels fill the SMs better):
+                # sum_k MSE_k / accum has the same gradient either way.
+                ck = c.detach().clone().requires_grad_(True)
+                x0, t, noise = (torch.cat([i[key] for i in ins]) for key in ("x0", "t", "noise"))
+                eps = unet_forward_train(step.unet, step.q_sample(x0, t, noise), t, ck, dict(step.extra_info))
+                per = eps.shape[0] // n
+                ls = [distill_loss(eps[k * per:(k + 1) * per], i["teacher_eps"]) for k, i in enumerate(ins)]
+                (g,) = torch.autograd.grad(sum(ls), ck)
+                c.backward(g * (1.0 / self.accum))
+                return torch.stack([l.detach() for l in ls])
             for k, i in enumerate(ins):
                 ck = c.detach()[k * rows:(k + 1) * rows].clone().requires_grad_(True)
                 eps = unet_forward_train(step.unet, step.q_sample(i["x0"], i["t"], i["noise"]), i["t"], ck,

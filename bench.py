@@ -250,7 +250,9 @@ def train_leg(dev, unet, world, rank, steps):
             "collective": "one NCCL all-reduce (SUM -> mean) of the flat fp32 gradient bucket per optimizer step" if world > 1 else None,
             "trainable_params": n_params, "loss": float(out["loss"]), "grad_norm": float(out["grad_norm"]),
             "config": {"workload": "stage1_distill_bs4x2accum_64x64", "micro_batch": 4, "grad_accum": 2,
-                       "optimizer": "Prodigy", "clip_grad_norm": 0.5, "cuda_graph": "one graph per micro-batch (conditioning + UNet forward and backward)",
+                       "optimizer": "Prodigy", "clip_grad_norm": 0.5, "cuda_graph": "one graph per optimizer step",
+                       "execution": "the 2 x 4 samples of the accumulation loop run through the conditioning and the frozen UNet as one "
+                                    "batch of 8 (same gradient of sum_k MSE_k / 2; tests/test_train_gpu.py compares with the loop)",
                        "teacher_eps": "fixed random tensor (SURVEY.md 8(d) config 4)"}}
     del trainer, step, params
     torch.cuda.empty_cache()

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--latent", type=int, default=64)
     ap.add_argument("--no-graph", action="store_true", help="eager autograd tape instead of the CUDA graph")
     ap.add_argument("--unet-graph", action="store_true", help="only the UNet forward + backward as a graph (round-2 first form)")
+    ap.add_argument("--loop-unet", action="store_true", help="step graph with the UNet run per micro-batch instead of fused")
     ap.add_argument("--breakdown", action="store_true", help="per-entry-point CUDA-event times of one optimizer step (stderr)")
     args = ap.parse_args()
     import torch.distributed as dist
@@ -45,6 +46,8 @@ def main():
     step, params = stage1_stack(dev)
     n_params = sum(p.numel() for p in params)
     trainer = Stage1Trainer(step, params, world_size=world, accum=args.accum, use_graph=False if args.no_graph else (True if args.unet_graph else "step"))
+    if args.loop_unet and trainer._gstep is not None:
+        trainer._gstep.fuse_unet = False
     g = torch.Generator().manual_seed(100 + rank)
 
     def optimizer_step(time_allreduce=False):
@@ -92,7 +95,8 @@ def main():
                           "config": {"workload": "stage1_distill_bs4x2accum_64x64", "micro_batch": args.bs,
                                      "grad_accum": args.accum, "latent": [4, args.latent, args.latent],
                                      "trainable_params": n_params, "optimizer": "Prodigy", "clip_grad_norm": 0.5,
-                                     "cuda_graph": "none" if args.no_graph else ("unet" if args.unet_graph else "micro-batch"),
+                                     "cuda_graph": "none" if args.no_graph else ("unet" if args.unet_graph else "optimizer step"),
+                                     "micro_batches_fused_through_unet": not (args.no_graph or args.unet_graph or args.loop_unet),
                                      "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0},
                           "loss": float(out["loss"]), "grad_norm": float(out["grad_norm"]),
                           "prodigy_d": trainer.optimizer.param_groups[0]["d"],
