@@ -90,6 +90,8 @@ def _splitk_workspace(device) -> Optional[torch.Tensor]:
     zeroed once - the kernel leaves the flag region zero.  Nothing is allocated while a capture is in progress: the
     eager warm-up that precedes every capture creates both."""
     capturing = torch.cuda.is_current_stream_capturing()
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
     st = _splitk_ws.get(device.index)
     if capturing:
         return st["graph"] if st is not None else None

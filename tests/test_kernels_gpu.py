@@ -642,11 +642,10 @@ def test_split_k_replays_from_a_cuda_graph():
     side.wait_stream(torch.cuda.current_stream())
     ops.conv3x3(x, w, out)                     # an eager launch creates the workspaces outside the capture
     eager = out.clone()
-    big = torch.empty(1 << 28, device=DEV)
-    for _ in range(4):
-        big.normal_()                          # keeps the first stream busy for a few milliseconds
+    torch.cuda._sleep(400_000_000)             # keeps the first stream busy for ~0.2 s
     with torch.cuda.stream(side):              # a second eager stream gets the whole-tile schedule while the first has
-        side_out = torch.empty_like(out)       # work in flight (see ops._splitk_workspace)
+        assert ops._splitk_workspace(out.device) is None              # work in flight (see ops._coop_state)
+        side_out = torch.empty_like(out)
         ops.conv3x3(x, w, side_out)
     torch.cuda.current_stream().wait_stream(side)
     g = torch.cuda.CUDAGraph()
