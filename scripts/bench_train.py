@@ -58,17 +58,21 @@ def main():
         out = optimizer_step()
     torch.cuda.synchronize()
     if args.breakdown and rank == 0:
-        eager = Stage1Trainer(step, params, world_size=1, accum=args.accum, use_graph=False, optimizer=trainer.optimizer)
-        batches = [stage1_batch(dev, args.bs, args.latent, g) for _ in range(args.accum)]
+        # the fused step = one eager pass over bs x accum samples (what the step graph holds)
+        fused = not (args.no_graph or args.unet_graph or args.loop_unet)
+        eager = Stage1Trainer(step, params, world_size=1, accum=1 if fused else args.accum, use_graph=False,
+                              optimizer=trainer.optimizer)
+        batches = ([stage1_batch(dev, args.bs * args.accum, args.latent, g)] if fused else
+                   [stage1_batch(dev, args.bs, args.latent, g) for _ in range(args.accum)])
         eager.optimizer_step(batches)
         with _lib.profile() as prof:
             eager.optimizer_step(batches)
         summ = prof.summary()
         tot = sum(v["ms"] for v in summ.values())
         print(f"one EAGER optimizer step: {sum(v['launches'] for v in summ.values())} C-ABI calls, {tot:.1f} ms of kernel time", file=sys.stderr)
-        for n, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])[:16]:
+        for n, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])[:24]:
             print(f"  {n:28s} x{v['launches']:5d} {v['ms']:8.2f} ms  {v['flops'] / max(v['ms'], 1e-9) / 1e9:7.1f} TFLOP/s", file=sys.stderr)
-        for n, v in sorted(prof.by_shape.items(), key=lambda kv: -kv[1]["ms"])[:24]:
+        for n, v in sorted(prof.by_shape.items(), key=lambda kv: -kv[1]["ms"])[:40]:
             print(f"    {n:60s} x{v['launches']:4d} {v['ms']:8.2f} ms", file=sys.stderr)
     if world > 1:
         dist.barrier()
