@@ -644,7 +644,7 @@ def test_split_k_replays_from_a_cuda_graph():
     eager = out.clone()
     torch.cuda._sleep(400_000_000)             # keeps the first stream busy for ~0.2 s
     with torch.cuda.stream(side):              # a second eager stream gets the whole-tile schedule while the first has
-        assert ops._splitk_workspace(out.device) is None              # work in flight (see ops._coop_state)
+        assert ops._splitk_workspace(out.device) is None              # work in flight (see ops._splitk_workspace)
         side_out = torch.empty_like(out)
         ops.conv3x3(x, w, side_out)
     torch.cuda.current_stream().wait_stream(side)
