@@ -52,3 +52,17 @@ if part:
         b0, b1 = int(t[c, best, EXP0]) - t0, int(t[c, best, EXP1]) - t0
         ov = max(0, min(a1, b1) - max(a0, b0))
         print(f"  j={j}: CTA0 exp [{a0},{a1})  CTA{c} j={best} exp [{b0},{b1})  overlap {ov}")
+    # exp-phase duration of CTA 0 against how much of it the partner was exponentiating too
+    ivs = [(int(t[c, jj, EXP0]) - t0, int(t[c, jj, EXP1]) - t0) for jj in range(min(nb, 64))]
+    rows = []
+    for j in range(2, min(nb, 64) - 1):
+        a0, a1 = int(t[0, j, EXP0]) - t0, int(t[0, j, EXP1]) - t0
+        ov = sum(max(0, min(a1, b1) - max(a0, b0)) for b0, b1 in ivs)
+        per = int(t[0, j + 1, 0]) - int(t[0, j, 0])
+        rows.append((j, a1 - a0, ov, per))
+    print("block: exp duration, overlap with the partner's exp phases, block period")
+    print("  " + "  ".join(f"{j}:{dur}/{ov}/{per}" for j, dur, ov, per in rows))
+    lo_ov = [r for r in rows if r[2] < 0.2 * r[1]]
+    hi_ov = [r for r in rows if r[2] > 0.8 * r[1]]
+    if lo_ov: print(f"  blocks with < 20 % overlap: n={len(lo_ov)} mean exp {st.mean(r[1] for r in lo_ov):.0f} period {st.mean(r[3] for r in lo_ov):.0f}")
+    if hi_ov: print(f"  blocks with > 80 % overlap: n={len(hi_ov)} mean exp {st.mean(r[1] for r in hi_ov):.0f} period {st.mean(r[3] for r in hi_ov):.0f}")
