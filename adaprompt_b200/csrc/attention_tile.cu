@@ -102,6 +102,12 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
   // reference is 0 whenever the first block's maximum lies inside the window.  P <= 2^64 in bf16, O <= 2^64 * Nk * |v|
   // in fp32; scores more than 2^-62 below the row maximum are irrelevant.
   constexpr float kWindow = 64.0f;
+  // GUARDLESS (d = 40, no mask): the fast path carries no per-block overflow guard at all - 87 of the ~555 instructions a
+  // softmax warp issues per key block, and that warp's issue rate is what bounds the kernel (profiles/r02_attention.md).
+  // Instead the row sums and the O accumulators are checked for inf / NaN once, at the end of the tile (any overflow of
+  // P, l or O propagates there), and a tile that trips is run a second time on the general path.
+  constexpr bool GUARDLESS = D == 40 && !MASKED;
+  constexpr int kPasses = GUARDLESS ? 2 : 1;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -117,6 +123,7 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
   uint64_t* p_full = s_free + 1;               // P_j in TMEM
   uint64_t* pv_done = p_full + 1;              // the MMAs of PV_j are complete (P buffer and O reusable)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  volatile int* redo = reinterpret_cast<volatile int*>(tmem_slot + 1);   // GUARDLESS: the tile overflowed, run it again
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -162,6 +169,7 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
     mbar_init(p_full, 4);
     mbar_init(pv_done, 1);
     mbar_fence_init();
+    *redo = 0;
   }
   // constant rows of every V^T stage: row D = 1.0 (column D of O becomes the row sum), rows D+1 .. DV-1 = 0.
   // A row of equal values is invariant under the 128-byte swizzle; the TMA box never touches these rows.
@@ -193,8 +201,14 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
 #pragma unroll
         for (int a = 0; a < KA; ++a)
           tma_load_3d(smem + S::kQOff + a * 128 * 128, &p.tmQ, q_full, h * p.dp + a * 64, q0, b);
-        int ks = 0, vs = 0;
-        uint32_t kph = 0, vph = 0;
+      }
+    }
+    // K / V ring positions, accumulator parities and the running block index survive a second pass over the tile
+    int ks = 0, vs = 0, kslot = 0, vslot = 0, gj = 0;
+    uint32_t kph = 0, vph = 0, kph_i = 0, vph_i = 0;
+    for (int pass = 0; pass < kPasses; ++pass) {
+    if (warp == 0) {
+      if (lane == 0) {
         for (int j = 0; j < n_blocks; ++j) {
           stamp(3, j, 0);
           mbar_wait_lean(&k_empty[ks], kph ^ 1);
@@ -225,14 +239,12 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN);
       const uint32_t q_addr = smem_base + S::kQOff;
       const uint32_t tm_s = tmem_base + C::kTmemS;
-      mbar_wait_lean(q_full, 0);
-      int kslot = 0;
-      uint32_t kph = 0;
-      for (int j = 0; j < n_blocks; ++j) {
+      if (pass == 0) mbar_wait_lean(q_full, 0);
+      for (int j = 0; j < n_blocks; ++j, ++gj) {
         stamp(2, j, 0);
-        mbar_wait_lean(&k_full[kslot], kph);
+        mbar_wait_lean(&k_full[kslot], kph_i);
         stamp(2, j, 1);
-        if (j > 0) mbar_wait_lean(s_free, (j - 1) & 1);
+        if (gj > 0) mbar_wait_lean(s_free, (gj - 1) & 1);
         tc_fence_after();
         stamp(2, j, 2);
         const uint32_t k_addr = smem_base + S::kKOff + kslot * S::kKBytes;
@@ -248,19 +260,17 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
         }
         __syncwarp();
         stamp(2, j, 3);
-        if (++kslot == C::KSTAGES) { kslot = 0; kph ^= 1; }
+        if (++kslot == C::KSTAGES) { kslot = 0; kph_i ^= 1; }
       }
     } else if (warp == 2) {
       // ------------------------------------------------------------------ PV issuer: O += P_j V_j once P_j is in TMEM
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, DV);
       const uint32_t tm_o = tmem_base + C::kTmemO, tm_p = tmem_base + C::kTmemP;
-      int vslot = 0;
-      uint32_t vph = 0;
-      for (int j = 0; j < n_blocks; ++j) {
-        mbar_wait_lean(&v_full[vslot], vph);
+      for (int j = 0; j < n_blocks; ++j, ++gj) {
+        mbar_wait_lean(&v_full[vslot], vph_i);
         stamp(2, j, 4);
         const uint32_t v_addr = smem_base + S::kVOff + vslot * S::kVBytes;
-        mbar_wait_lean(p_full, j & 1);
+        mbar_wait_lean(p_full, gj & 1);
         tc_fence_after();
         stamp(2, j, 5);
         if (elect_one()) {
@@ -274,9 +284,18 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
         }
         __syncwarp();
         stamp(2, j, 6);
-        if (++vslot == C::VSTAGES) { vslot = 0; vph ^= 1; }
+        if (++vslot == C::VSTAGES) { vslot = 0; vph_i ^= 1; }
       }
     }
+    if constexpr (GUARDLESS) {
+      if (pass == 0) {
+        tc_fence_before();
+        __syncthreads();                 // the softmax warps have judged the tile (and read O)
+        tc_fence_after();
+        if (*redo == 0) break;
+      }
+    }
+    }  // pass
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ------------------------------------------------------------------ softmax: one thread per query row
@@ -291,8 +310,10 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
     const uint32_t a_s_full = smem_u32(s_full), a_s_free = smem_u32(s_free);
     const uint32_t a_p_full = smem_u32(p_full), a_pv_done = smem_u32(pv_done);
     const bool tw = TRACE && warp == 4;
+    uint32_t par = 0;                             // running block index & 1 (survives a second pass)
+    for (int pass = 0; pass < kPasses; ++pass) {
+    const bool safe = pass != 0;                  // second pass of a tile that overflowed: general path only
     float m_ref = -INFINITY;
-    uint32_t par = 0;                             // j & 1
     for (int j = 0; j < n_blocks; ++j, par ^= 1) {
       if (tw) stamp(0, j, 0);
       mbar_wait_lean(a_s_full, par);
@@ -340,8 +361,8 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
         return fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
                      fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
       };
-      auto wait_p_free = [&]() {                  // the P buffer has been consumed by PV_{j-1}
-        if (j > 0) {
+      auto wait_p_free = [&]() {                  // the P buffer has been consumed by the previous PV
+        if (j > 0 || pass > 0) {
           mbar_wait_lean(a_pv_done, par ^ 1);
           tc_fence_after();
         }
@@ -367,13 +388,13 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
       // exponentials do not depend on the block maximum, so they are issued straight away and the maximum is only the
       // overflow guard, computed next to them (ALU pipe under the MUFU queue) instead of in front of them.  A guard trip
       // re-does the block on the general path (P is rewritten before it is handed over).
-      bool fast = __all_sync(0xffffffffu, m_ref == 0.f);
+      bool fast = !safe && __all_sync(0xffffffffu, m_ref == 0.f);
       if (fast) {
         if (tw) stamp(0, j, 3);
         wait_p_free();
         if (tw) stamp(0, j, 4);
         exp_block(std::false_type{}, 0.f);
-        fast = !__any_sync(0xffffffffu, block_max() > kWindow);
+        if constexpr (!GUARDLESS) fast = !__any_sync(0xffffffffu, block_max() > kWindow);
       }
       if (!fast) {
         release_s();
@@ -414,7 +435,7 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
       if (tw) stamp(0, j, 6);
     }
     // epilogue: l = column D of O; O / l -> bf16
-    mbar_wait_lean(a_pv_done, (n_blocks - 1) & 1);
+    mbar_wait_lean(a_pv_done, par ^ 1);           // the last block's PV
     tc_fence_after();
     float l_tot;
     {
@@ -423,6 +444,39 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
       tmem_ld_wait();
       l_tot = __uint_as_float(lv[0]);
     }
+    if constexpr (GUARDLESS) {
+      // whole O row in registers: judged first (pass 0), written after the CTA-wide decision
+      uint32_t o[DV];
+#pragma unroll
+      for (int c = 0; c < DV; c += 16) tmem_ld16(o_addr + c, *reinterpret_cast<uint32_t (*)[16]>(o + c));
+      tmem_ld_wait();
+      if (pass == 0) {
+        uint32_t worst = __float_as_uint(l_tot) & 0x7f800000u;       // exponent 255 <=> inf / NaN
+#pragma unroll
+        for (int c = 0; c < D; ++c) worst = max(worst, o[c] & 0x7f800000u);
+        if (__any_sync(0xffffffffu, worst == 0x7f800000u) && lane == 0) *redo = 1;
+        tc_fence_before();
+        __syncthreads();                          // with the service warps: everybody reads the same verdict
+        tc_fence_after();
+        if (*redo != 0) continue;                 // run the tile again on the general path
+      }
+      const float inv_l = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+      if (p.lse != nullptr && q_row < p.Nq)
+        p.lse[(static_cast<size_t>(b) * p.heads + h) * p.Nq + q_row] = l_tot > 0.f ? m_ref + __log2f(l_tot) : INFINITY;
+      if (q_row < p.Nq) {
+        __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * p.Nq + q_row) * p.ldo + h * p.d;
+#pragma unroll
+        for (int c = 0; c < D; c += 8) {
+          uint4 pk;
+          pk.x = pack_bf16x2(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+          pk.y = pack_bf16x2(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+          pk.z = pack_bf16x2(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+          pk.w = pack_bf16x2(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c) = pk;
+        }
+      }
+      break;
+    } else {
     const float inv_l = l_tot > 0.f ? 1.0f / l_tot : 0.f;
     if (p.lse != nullptr && q_row < p.Nq)
       p.lse[(static_cast<size_t>(b) * p.heads + h) * p.Nq + q_row] = l_tot > 0.f ? m_ref + __log2f(l_tot) : INFINITY;
@@ -446,6 +500,8 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
         }
       }
     }
+    }
+    }  // pass
   }
 
   tc_fence_before();

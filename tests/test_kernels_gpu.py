@@ -146,7 +146,9 @@ def test_conv3x3_dual_source_rowbias_residual():
 
 
 # ------------------------------------------------------------------------------------------------ attention
-def _attn_case(B, N, Nk, d, seed=0, mask=False, cross=False):
+def _attn_case(B, N, Nk, d, seed=0, mask=False, cross=False, boost=None):
+    """boost = (first_key, factor): keys from first_key on are scaled, so that scores far above the first block's appear
+    late in the key loop (the lazy-reference / overflow paths of the attention kernels)."""
     from adaprompt_b200 import ops
     heads = 8
     C = heads * d
@@ -155,6 +157,8 @@ def _attn_case(B, N, Nk, d, seed=0, mask=False, cross=False):
     q = _rand(B, N, heads, d, seed=seed + 1)
     k = _rand(B, Nk, heads, d, seed=seed + 2)
     v = _rand(B, Nk, heads, d, seed=seed + 3)
+    if boost is not None:
+        k[:, boost[0]:] *= boost[1]
     qs = (q * (scale * math.log2(math.e))).to(torch.bfloat16)
     kb, vb = k.to(torch.bfloat16), v.to(torch.bfloat16)
     qbuf = torch.zeros(B, N, heads, dp, device=DEV, dtype=torch.bfloat16)
@@ -185,6 +189,18 @@ def _attn_case(B, N, Nk, d, seed=0, mask=False, cross=False):
                                    (2, 144, 160), (1, 576, 160)])
 def test_self_attention(B, N, d):
     assert _attn_case(B, N, N, d) < 6e-3
+
+
+@pytest.mark.parametrize("B,N,d,first,factor", [
+    (1, 1024, 40, 640, 40.0),      # scores up to ~2^+-250 from key 640 on: P overflows on the unguarded fast path -> second pass
+    (1, 1024, 40, 640, 14.0),      # ~2^90: no overflow of P, but beyond the 2^64 window
+    (2, 1024, 80, 512, 30.0),      # d = 80 keeps the per-block guard
+    (1, 4096, 40, 3968, 60.0),     # only the LAST key block is extreme
+])
+def test_self_attention_large_scores_late_in_the_key_loop(B, N, d, first, factor):
+    """Rows whose maximum moves far away from the first block's: the result must be the exact softmax (no inf / NaN, no
+    stale reference) whichever path the kernel takes to get there."""
+    assert _attn_case(B, N, N, d, seed=11, boost=(first, factor)) < 8e-3
 
 
 @pytest.mark.parametrize("B,N,d", [(2, 4096, 40), (2, 1024, 80), (2, 256, 160), (2, 64, 160)])
