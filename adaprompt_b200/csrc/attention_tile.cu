@@ -391,9 +391,35 @@ __global__ void __launch_bounds__(256, 2) attention_tile_kernel(const __grid_con
       bool fast = !safe && __all_sync(0xffffffffu, m_ref == 0.f);
       if (fast) {
         if (tw) stamp(0, j, 3);
+        // The first kLate x 32 exponentials go to REGISTERS before the wait for the P buffer (PV_{j-1} may still be reading
+        // it): the wait - 360 cycles at the head of the chain before - hides behind them; every later chunk is stored as soon
+        // as it is computed (storing everything late was slower: the stores then drain at the tail of the block).
+#ifndef AF_TILE_LATE_CHUNKS
+#define AF_TILE_LATE_CHUNKS 2
+#endif
+        constexpr int kLate = AF_TILE_LATE_CHUNKS * 32 < BN ? AF_TILE_LATE_CHUNKS * 32 : BN / 2;
+        uint32_t pk0[kLate / 2];
+#pragma unroll
+        for (int c = 0; c < kLate; c += 32) {
+          if (c == 32) release_s();
+#pragma unroll
+          for (int e = 0; e < 32; e += 2)
+            pk0[(c + e) >> 1] = pack_bf16x2(tile_exp2<POLY>(e, sc[c + e]), tile_exp2<POLY>(e + 1, sc[c + e + 1]));
+        }
+        release_s();
+        if (tw) stamp(0, j, 2);
         wait_p_free();
         if (tw) stamp(0, j, 4);
-        exp_block(std::false_type{}, 0.f);
+#pragma unroll
+        for (int c = 0; c < kLate; c += 32) tile_st16(pt_addr + c / 2, *reinterpret_cast<uint32_t (*)[16]>(&pk0[c >> 1]));
+#pragma unroll
+        for (int c = kLate; c < BN; c += 32) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2)
+            pk[e >> 1] = pack_bf16x2(tile_exp2<POLY>(e, sc[c + e]), tile_exp2<POLY>(e + 1, sc[c + e + 1]));
+          tile_st16(pt_addr + c / 2, pk);
+        }
         if constexpr (!GUARDLESS) fast = !__any_sync(0xffffffffu, block_max() > kWindow);
       }
       if (!fast) {
