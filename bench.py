@@ -476,6 +476,19 @@ def main():
             roofline["attention"] = {"bound": "tensor", "achieved": tf, "peak": peaks["tflops_sustained"],
                                      "unit": "TFLOP/s", "frac": tf / peaks["tflops_sustained"],
                                      "share_of_unet_step": at["ms"] / step_ms}
+            hot = prof.by_shape.get(f"attention_bf16 B{2 * b} Nq{LATENT * LATENT} Nk{LATENT * LATENT} d40")
+            if hot and hot["ms"] > 0:      # the long-sequence self-attention launches alone (3/4 of the class's time)
+                htf = hot["flops"] / (hot["ms"] * 1e-3) / 1e12
+                roofline["attention"]["self_attention_64x64_d40"] = {
+                    "launches": hot["launches"], "ms_each": hot["ms"] / hot["launches"], "achieved": htf,
+                    "frac": htf / peaks["tflops_sustained"]}
+        for cls, key in (("af_conv3x3_bf16", "conv3x3"), ("af_gemm_bf16", "gemm")):
+            v = breakdown.get(cls)
+            if v and v["ms"] > 0:          # both tensor-core classes, whichever of them is the dominant kernel above
+                ctf = v["flops"] / (v["ms"] * 1e-3) / 1e12
+                roofline[key] = {"bound": "tensor", "achieved": ctf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                                 "frac": ctf / peaks["tflops_sustained"], "launches": v["launches"],
+                                 "share_of_unet_step": v["ms"] / step_ms}
         roofline["unet_step_ms_eager_sum"] = step_ms
         if args.breakdown:
             for n, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"]):
