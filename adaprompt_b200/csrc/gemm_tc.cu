@@ -57,6 +57,7 @@ struct GemmParams {
   void* out;
   long long ldo;
   int out_bf16;
+  int wide;                // bf16 output without residual, BN % 128 == 0: 64-column epilogue items (128-byte rows)
   long long* trace;        // optional timeline of CTA 0: [3 actors][32 tiles][8 events] clock64 (af_epilogue.trace)
   int geglu;               // tile cols [0,BN/2) = value, [BN/2,BN) = gate; writes BN/2 cols
   int act;                 // 0 none, 1 quick_gelu x*sigmoid(1.702x) on (acc + bias), before the residual add
@@ -522,6 +523,84 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         }
       }
 
+      if (!GEGLU && p.wide) {
+        // 64-column items for bf16 outputs: the two 32-column halves go through registers one after the other, but the
+        // slot hand-over, proxy fence, warp sync and TMA store are paid once per 128-byte row instead of once per 64 bytes.
+        // The short-K projections (QK, V^T: 5 K blocks per tile) are bound by exactly those per-item costs.
+        const int nchw = (kOutCols - half * 64 + 127) / 128;
+        for (int i = 0; i < nchw; ++i) {
+          const int c = half * 64 + 128 * i;
+          const int col0 = n_tile * kOutCols + c;
+          uint8_t* slot = my_slots + (item % SLOTS) * Cfg::kSlotBytes;
+          const uint32_t slot_a = smem_u32(slot);
+          if (elect_one()) bulk_wait_read<SLOTS - 1>();        // the store that last used this slot has read it
+          __syncwarp();
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            uint32_t v[32];
+            tmem_ld32(t_acc + c + 32 * sub, v);
+            const int cs = col0 + 32 * sub;
+            float4 b4[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (cs + 4 * j < p.N) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + cs) + j);
+            }
+            if (rb_row) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (cs + 4 * j < p.N) {
+                  const float4 rb = __ldg(reinterpret_cast<const float4*>(rb_row + cs) + j);
+                  b4[j].x += rb.x; b4[j].y += rb.y; b4[j].z += rb.z; b4[j].w += rb.w;
+                }
+              }
+            }
+            tmem_ld_wait();
+            if (ws_row != nullptr) {   // finisher of a split tile: + the partial accumulators, in K-range order
+              constexpr int kTileF4 = 128 * (BN / 4);
+              for (int sp = 0; sp < p.split - 1; ++sp) {
+                const float4* src = ws_row + static_cast<size_t>(sp) * kTileF4 + ((c + 32 * sub) >> 5) * 8 * 128;
+                float4 part[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) part[j] = __ldcg(src + j * 128);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + part[j].x);
+                  v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + part[j].y);
+                  v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + part[j].z);
+                  v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + part[j].w);
+                }
+              }
+            }
+            float4 o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[j] = make_float4(__uint_as_float(v[4 * j]) + b4[j].x, __uint_as_float(v[4 * j + 1]) + b4[j].y,
+                                 __uint_as_float(v[4 * j + 2]) + b4[j].z, __uint_as_float(v[4 * j + 3]) + b4[j].w);
+            if (p.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                o[j].x = quick_gelu(o[j].x); o[j].y = quick_gelu(o[j].y);
+                o[j].z = quick_gelu(o[j].z); o[j].w = quick_gelu(o[j].w);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)     // 16-byte chunk (sub * 4 + j) of the lane's 128-byte row, SWIZZLE_128B
+              sts128(slot_a + lane * 128 + (((sub * 4 + j) ^ (lane & 7)) << 4), pack_bf16x2(o[2 * j].x, o[2 * j].y),
+                     pack_bf16x2(o[2 * j].z, o[2 * j].w), pack_bf16x2(o[2 * j + 1].x, o[2 * j + 1].y),
+                     pack_bf16x2(o[2 * j + 1].z, o[2 * j + 1].w));
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (elect_one()) {
+            if (col0 < p.N) tma_store_4d(&p.tmOut, slot, col0, c1, c2, c3);
+            bulk_commit();
+          }
+          ++item;
+        }
+      } else
       // (Fetching chunk i+1 from TMEM into a second register set while chunk i is staged was measured SLOWER: 48.7 ->
       // 59.4 us on M65536 N320 K320 +res, the conversion phase doubles - profiles/r01_gemm_epilogue_timeline.md.)
       for (int i = 0; i < nch; ++i) {
@@ -842,7 +921,7 @@ static int make_epilogue_maps(GemmParams& p, int out_cols, bool conv) {
   dims[0] = static_cast<uint64_t>(out_cols);
   if (!conv) {
     dims[1] = static_cast<uint64_t>(p.M); dims[2] = 1; dims[3] = 1;
-    box[0] = 32; box[1] = 32; box[2] = 1; box[3] = 1;
+    box[0] = p.wide ? 64 : 32; box[1] = 32; box[2] = 1; box[3] = 1;
     p.sbx = 32; p.sby = 1;
     ostr[0] = p.ldo * oes; ostr[1] = ostr[0] * dims[1]; ostr[2] = ostr[1];
     rstr[0] = p.ldr * 4; rstr[1] = rstr[0] * dims[1]; rstr[2] = rstr[1];
@@ -852,11 +931,11 @@ static int make_epilogue_maps(GemmParams& p, int out_cols, bool conv) {
     int sby = p.bh < 32 / sbx ? p.bh : 32 / sbx;
     int sbz = 32 / (sbx * sby);
     p.sbx = sbx; p.sby = sby;
-    box[0] = 32; box[1] = sbx; box[2] = sby; box[3] = sbz;
+    box[0] = p.wide ? 64 : 32; box[1] = sbx; box[2] = sby; box[3] = sbz;
     ostr[0] = p.ldo * oes; ostr[1] = ostr[0] * p.W; ostr[2] = ostr[1] * p.H;
     rstr[0] = p.ldr * 4; rstr[1] = rstr[0] * p.W; rstr[2] = rstr[1] * p.H;
   }
-  int rc = make_tmap(&p.tmOut, p.out, oes, p.out_bf16 ? 64 : 128, 4, dims, ostr, box);
+  int rc = make_tmap(&p.tmOut, p.out, oes, (p.out_bf16 && !p.wide) ? 64 : 128, 4, dims, ostr, box);
   if (rc) return rc;
   p.tmRes = p.tmOut;
   if (p.residual) {
@@ -975,6 +1054,9 @@ extern "C" int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* 
   p.n_tiles = (N + bn - 1) / bn;
   int rc = fill_epilogue(p, ep, ep->geglu ? N / 2 : N);
   if (rc) return rc;
+#ifndef AF_GEMM_NO_WIDE
+  p.wide = p.out_bf16 && !p.geglu && p.residual == nullptr && (bn == 128 || bn == 256);
+#endif
   rc = make_epilogue_maps(p, ep->geglu ? N / 2 : N, false);
   if (rc) return rc;
   plan_split(p, bn, pair, ep);
@@ -1072,6 +1154,9 @@ extern "C" int af_conv3x3_bf16(const void* X0, int C0, const void* X1, int C1, c
     p.gn_slots = af_conv3x3_gn_slots(Ho, Wo);
     AF_CHECK_ARG(p.gn_slots > 0, "af_conv3x3_bf16: gn_stats unsupported for %dx%d outputs (fewer than 32 pixels per tile row group)", Ho, Wo);
   }
+#ifndef AF_GEMM_NO_WIDE
+  p.wide = p.out_bf16 && p.residual == nullptr && (bn == 128 || bn == 256);
+#endif
   rc = make_epilogue_maps(p, Cout, true);
   if (rc) return rc;
   plan_split(p, bn, pair, ep);
