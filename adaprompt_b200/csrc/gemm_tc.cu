@@ -841,13 +841,22 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   return 0;
 }
 
-// Measured on B200 (profiles/r01_pair_vs_single.md): the pair schedule wins for linear GEMMs with N tiles >= 160 and
-// at least two waves of pair tiles (+7 % on the FF2 shapes, +17 % on 8192^3 with 256-wide tiles) and loses ~3 % on the
-// implicit-GEMM convolutions, so mode 1 ("auto") uses it only there; mode 2 forces it wherever it is legal (tests).
+// CTA pairs (cta_group::2: two SMs share one 256-row tile, each stages half of the weight tile).  Re-measured per shape
+// with the round-2 kernel (scripts/bench_pair.py, profiles/r02_splitk.md): the pair schedule wins for linear GEMMs from
+// 32 row tiles up (M >= 4096: -2 .. -8 %) and - unlike in round 1, before the producer split - for the stride-1
+// convolutions with 160-wide tiles and >= 128 row tiles (64x64: -9 .. -12 %, 32x32 to 640 channels: -3 .. -5 %); it
+// loses where the tile count is small (16x16 / 8x8: those go to split-K, which the pair schedule does not do).
+// Mode 1 ("auto") applies that; mode 2 forces pairs wherever they are legal (tests).
 static bool want_pair(int pair_mode, int m_tiles, int n_tiles, int bn, int amode) {
+  (void)n_tiles;
   if (pair_mode == AF_PAIR_NEVER || m_tiles < 2) return false;
   if (pair_mode == AF_PAIR_ALWAYS) return true;
+#ifdef AF_PAIR_R1_RULE
   return amode == 0 && bn >= 160 && ((m_tiles + 1) / 2) * n_tiles >= num_sms();
+#endif
+  if (amode == 0) return bn >= 160 && m_tiles >= 32;
+  if (amode == 1) return bn == 160 && m_tiles >= 128;
+  return false;
 }
 
 template <int BN, bool GEGLU, int SLOTS>
