@@ -843,7 +843,7 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
 
 // CTA pairs (cta_group::2: two SMs share one 256-row tile, each stages half of the weight tile).  Re-measured per shape
 // with the round-2 kernel (scripts/bench_pair.py, profiles/r02_splitk.md): the pair schedule wins for linear GEMMs from
-// 32 row tiles up (M >= 4096: -2 .. -8 %) and - unlike in round 1, before the producer split - for the stride-1
+// 16 row tiles up (M >= 2048: -2 .. -12 %; at 8 row tiles split-K is worth more) and - unlike in round 1, before the producer split - for the stride-1
 // convolutions with 160-wide tiles and >= 128 row tiles (64x64: -9 .. -12 %, 32x32 to 640 channels: -3 .. -5 %) or with
 // any tile width >= 128 from 512 row tiles (the VAE decoder's 128^2 .. 512^2 layers: -5 .. -10 %); it
 // loses where the tile count is small (16x16 / 8x8: those go to split-K, which the pair schedule does not do).
@@ -855,7 +855,7 @@ static bool want_pair(int pair_mode, int m_tiles, int n_tiles, int bn, int amode
 #ifdef AF_PAIR_R1_RULE
   return amode == 0 && bn >= 160 && ((m_tiles + 1) / 2) * n_tiles >= num_sms();
 #endif
-  if (amode == 0) return bn >= 160 && m_tiles >= 32;
+  if (amode == 0) return bn >= 160 && m_tiles >= 16;
   if (amode == 1) return (bn == 160 && m_tiles >= 128) || (bn >= 128 && m_tiles >= 512);   // the second clause: VAE decoder layers
   return false;
 }
