@@ -61,6 +61,9 @@ SIGNATURES = {
                              POINTER(AfEpilogue), c_int, c_void_p]),
     "af_conv3x3_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                 POINTER(AfEpilogue), c_int, c_void_p]),
+    "af_gemm_plan": (c_int, [c_int, c_int, c_int, POINTER(AfEpilogue), c_int, POINTER(c_int)]),
+    "af_conv3x3_plan": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(AfEpilogue), c_int,
+                                POINTER(c_int)]),
     "af_attention_bf16": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_void_p,
                                   c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "af_conv3x3_gn_slots": (c_int, [c_int, c_int]),
@@ -135,7 +138,7 @@ class AdaFaceB200Error(RuntimeError):
     pass
 
 
-ABI_VERSION = 201      # include/adaface_b200.h AF_VERSION
+ABI_VERSION = 202      # include/adaface_b200.h AF_VERSION
 
 
 def load():

@@ -1172,3 +1172,66 @@ extern "C" int af_conv3x3_bf16(const void* X0, int C0, const void* X1, int C1, c
   plan_split(p, bn, pair, ep);
   return dispatch_gemm(bn, p, pair, stream);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Schedule introspection (no launch, no device needed: 148 SMs are assumed without one): the tile width, tile schedule
+// and split-K plan af_gemm_bf16 / af_conv3x3_bf16 would use - the same pick_bn / want_pair / plan_split calls.
+// out[0] = N-tile width, out[1] = 1 if CTA pairs, out[2] = K ranges per remainder tile (1 = whole tiles),
+// out[3] = work units, out[4] = whole-K tiles before the split ones, out[5] = 1 if 64-column bf16 epilogue items.
+// ---------------------------------------------------------------------------------------------
+static void fill_plan(const GemmParams& p, int bn, bool pair, int* out) {
+  out[0] = bn;
+  out[1] = pair ? 1 : 0;
+  out[2] = p.split;
+  out[3] = p.num_units;
+  out[4] = p.dp_tiles;
+  out[5] = p.wide;
+}
+
+extern "C" int af_gemm_plan(int M, int N, int K, const af_epilogue* ep, int bn_hint, int* out) {
+  AF_CHECK_ARG(ep && out && M > 0 && N > 0 && K > 0, "af_gemm_plan: bad arguments");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int bn = pick_bn(N, ep->geglu, bn_hint, K, ep->residual != nullptr, false, (M + 127) / 128);
+  const bool pair = want_pair(ep->pair_mode, (M + 127) / 128, (N + bn - 1) / bn, bn, 0);
+  p.num_kb = (K + 63) / 64;
+  p.m_tiles = (M + 127) / 128;
+  p.n_tiles = (N + bn - 1) / bn;
+  p.geglu = ep->geglu;
+  p.residual = ep->residual;
+  p.out_bf16 = ep->out_dtype == AF_DTYPE_BF16;
+#ifndef AF_GEMM_NO_WIDE
+  p.wide = p.out_bf16 && !p.geglu && p.residual == nullptr && (bn == 128 || bn == 256);
+#endif
+  plan_split(p, bn, pair, ep);
+  fill_plan(p, bn, pair, out);
+  return 0;
+}
+
+extern "C" int af_conv3x3_plan(int C0, int C1, int B, int H, int W, int Cout, int stride, const af_epilogue* ep,
+                               int bn_hint, int* out) {
+  AF_CHECK_ARG(ep && out && B > 0 && H > 0 && W > 0 && Cout > 0 && C0 > 0 && (stride == 1 || stride == 2),
+               "af_conv3x3_plan: bad arguments");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int Cin = C0 + C1;
+  const int Ho = stride == 1 ? H : H / 2, Wo = stride == 1 ? W : W / 2;
+  int bw, bh, nb;
+  conv_tile_box(Ho, Wo, &bw, &bh, &nb);
+  const int m_tiles = ((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * ((B + nb - 1) / nb);
+  const int bn = pick_bn(Cout, 0, bn_hint, 9 * Cin, ep->residual != nullptr, true, m_tiles);
+  const bool pair = want_pair(ep->pair_mode, m_tiles, (Cout + bn - 1) / bn, bn, 1);
+  p.amode = stride == 1 ? 1 : 2;
+  p.num_kb = 9 * (Cin / 64);
+  p.m_tiles = m_tiles;
+  p.n_tiles = (Cout + bn - 1) / bn;
+  p.residual = ep->residual;
+  p.out_bf16 = ep->out_dtype == AF_DTYPE_BF16;
+#ifndef AF_GEMM_NO_WIDE
+  p.wide = p.out_bf16 && p.residual == nullptr && (bn == 128 || bn == 256);
+#endif
+  plan_split(p, bn, pair, ep);
+  fill_plan(p, bn, pair, out);
+  return 0;
+}
+

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AF_VERSION 201
+#define AF_VERSION 202
 #define AF_DTYPE_F32 0
 #define AF_DTYPE_BF16 1
 #define AF_GN_MAX_CHUNKS 64
@@ -86,6 +86,14 @@ typedef struct af_epilogue {
  * bn_hint: 0 = auto, or 64/128/160/256 (N tile). */
 int af_gemm_bf16(const void* A0, long long lda0, int K0, const void* A1, long long lda1, int K1, const void* Wt,
                  int M, int N, const af_epilogue* ep, int bn_hint, af_stream_t stream);
+
+/* Schedule introspection (no launch, no device needed - 148 SMs are assumed without one): what af_gemm_bf16 /
+ * af_conv3x3_bf16 would choose for these sizes and this epilogue.  out[0] = N-tile width, out[1] = 1 if CTA pairs,
+ * out[2] = K ranges per remainder tile (1 = whole tiles only), out[3] = work units, out[4] = whole-K tiles in front of the
+ * split ones, out[5] = 1 if the bf16 output leaves in 64-column epilogue items.  Host-side logic tests use these. */
+int af_gemm_plan(int M, int N, int K, const af_epilogue* ep, int bn_hint, int* out);
+int af_conv3x3_plan(int C0, int C1, int B, int H, int W, int Cout, int stride, const af_epilogue* ep, int bn_hint,
+                    int* out);
 
 /* 3x3 convolution, pad 1, stride 1 or 2, NHWC bf16 input(s) [B,H,W,C0] (+ [B,H,W,C1] concat), weights
  * Wt[Cout][ky][kx][C0+C1] bf16, as an implicit GEMM (no im2col buffer).  Output rows are output pixels
